@@ -1,0 +1,145 @@
+/*
+ * trajopt_b200 — C ABI of the B200-native batched DDP/iLQR solver on SO(3)/SE(3).
+ *
+ * The reference (chenghuailin/trajectory_optimization_matrix_lie_groups) is pure Python and has
+ * no FFI; its boundary is the class API of traoptlibrary.  The entry points below are what the
+ * Python controllers of the drop-in package bind through ctypes, one per reference call:
+ *
+ *   trajopt_create / trajopt_destroy      <- controller construction
+ *                                            traoptlibrary/traopt_controller.py:532-573 (iLQR_Tracking_SO3),
+ *                                            :1036-1128 (SO3_MS), :1837-1878 (SE3), :2359-2415 (SE3_MS),
+ *                                            :3145-3200 (AL_iLQR_Tracking_SE3_MS)
+ *   trajopt_set_params                    <- dynamics / cost / constraint objects handed to the controller
+ *                                            traopt_dynamics.py:279-327, 633-690, 1214-1278;
+ *                                            traopt_cost.py:297-329, 587-622, 1182-1209;
+ *                                            traopt_constraints.py:70-81;  fit() keyword arguments
+ *                                            traopt_controller.py:575-578, 1131-1133, 1880-1881, 2443-2445, 3218-3221
+ *   trajopt_set_reference                 <- q_ref / xi_ref of the tracking cost and of the MS initial guess
+ *                                            traopt_cost.py:614-616, 322-323; traopt_controller.py:2399-2400, 3123-3136
+ *   trajopt_begin                         <- start of fit(): regulariser reset, initial rollout / initial guess
+ *                                            traopt_controller.py:1899-1924, 2463-2491, 2015-2028, 3123-3136
+ *   trajopt_iterate                       <- the `for iteration in range(n_iterations)` loop body
+ *                                            traopt_controller.py:1926-2007 (SS), 2493-2633 (MS), 3231-3264 (AL outer)
+ *   trajopt_export / trajopt_export_hist  <- fit() return values and what the on_iteration callbacks record
+ *                                            traopt_controller.py:2013, 2639, 3266-3267; benchmark_SE3_tracking.py:22-42
+ *   trajopt_solve / trajopt_solve_host    <- one whole fit() for every problem of the batch; the batch itself
+ *                                            replaces the joblib pool of visualization/perturb_all_compute.py:240-250
+ *   trajopt_debug_*                       <- per-stage quantities (_linearization :2098-2176 / :2823-2910,
+ *                                            _backward_pass :2178-2261 / :2912-3006) exported for parity tests
+ *
+ * Conventions: FP64 throughout.  Pointers named d_* are device pointers, h_* host pointers.
+ * Poses cross the ABI as unit quaternion [x, y, z, w] (+ position [x, y, z] for SE3); twists are
+ * [omega, v].  A state row is  SE3/drone: q(4) p(3) xi(6) = 13 doubles,  SO3: q(4) w(3) = 7 doubles.
+ * Batched arrays are problem-major, C-contiguous:  x0 [B][NS], us [B][N][NU], xs [B][N+1][NS].
+ * Every function returns 0 on success, a negative TRAJOPT_E_* code otherwise; trajopt_last_error()
+ * returns a static description.  No exceptions cross the ABI.  A handle belongs to one device and
+ * is not thread-safe.  `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ */
+#ifndef TRAJOPT_B200_H
+#define TRAJOPT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { TRAJOPT_SO3 = 0, TRAJOPT_SE3 = 1, TRAJOPT_DRONE = 2 };
+enum { TRAJOPT_SS = 0, TRAJOPT_MS = 1, TRAJOPT_AL_MS = 2 };
+
+/* per-problem status (low 4 bits) and flags */
+enum {
+    TRAJOPT_CONVERGED = 0,   /* gradient (and defect) tolerance met                                  */
+    TRAJOPT_MAX_ITER = 1,    /* n_iterations exhausted                                               */
+    TRAJOPT_NO_DESCENT = 2,  /* "Couldn't find descent direction" (traopt_controller.py:2005-2007)   */
+    TRAJOPT_RUNNING = 3,     /* not finished yet (only visible between trajopt_iterate calls)        */
+    TRAJOPT_FLAG_REG_EXCEEDED = 16, /* "exceeded max regularization term" fired (:2238-2240)         */
+    TRAJOPT_FLAG_NONFINITE = 32     /* a cost or state became NaN/Inf                                */
+};
+
+enum {
+    TRAJOPT_E_INVALID = -1,  /* bad argument                                  */
+    TRAJOPT_E_CUDA = -2,     /* CUDA runtime error (see trajopt_last_error)   */
+    TRAJOPT_E_STATE = -3     /* call order violated (e.g. iterate before begin) */
+};
+
+typedef struct trajopt_handle trajopt_handle;
+
+/* Everything the reference spreads over Dynamics / Cost / Constraint / fit(**kwargs). Row-major. */
+typedef struct trajopt_params {
+    double dt;
+    double Ib[9];            /* body inertia, J[0:3,0:3] (traopt_dynamics.py:662)                       */
+    double mass;             /* J[4,4] (traopt_dynamics.py:663)                                        */
+    double gravity;          /* DroneDynamics._g = 9.8 (traopt_dynamics.py:1245); ignored otherwise    */
+    double Q[144];           /* stage weight  [NX][NX]; only the two diagonal NPxNP blocks are read    */
+    double P[144];           /* terminal weight [NX][NX]                                               */
+    double R[36];            /* control weight [NU][NU]                                                */
+    double lb[6], ub[6];     /* InputConstraint bounds (AL only)                                       */
+    int32_t has_constraints;
+    int32_t rollout_linear;  /* rollout='linear' (1) / 'nonlinear' (0)                                 */
+    int32_t line_search;     /* MS merit line search (traopt_controller.py:2549-2590)                  */
+    int32_t n_alphas;        /* 13 (SS, SO3-MS) or 20 (SE3-MS); 0 = class default                      */
+    int32_t max_iters;       /* n_iterations                                                           */
+    double tol_grad_norm;
+    double tol_d_norm;
+    double max_reg;          /* 1e10; <= 0 disables the give-up test like max_reg=None                 */
+    double defect_kappa;     /* 1e-12 (SE3-MS) / 1e-14 (SO3-MS); 0 = class default                     */
+    /* augmented Lagrangian outer loop (traopt_controller.py:3182-3184, 3218-3221) */
+    int32_t n_al_iters;
+    double al_mu0, al_mu_scale, al_mu_max, tol_constr;
+} trajopt_params;
+
+const char* trajopt_last_error(void);
+int trajopt_version(void);
+
+int trajopt_create(int kind, int method, int N, int B, int device, trajopt_handle** out);
+int trajopt_destroy(trajopt_handle* h);
+int trajopt_set_params(trajopt_handle* h, const trajopt_params* p);
+/* h_q_ref [N+1][7] (SE3/drone) or [N+1][4] (SO3), h_xi_ref [N+1][6|3]; host pointers, shared by the batch */
+int trajopt_set_reference(trajopt_handle* h, const double* h_q_ref, const double* h_xi_ref);
+
+/* us_mode: 0 = zeros (d_us_init ignored), 1 = one [N][NU] path shared by the batch, 2 = [B][N][NU] */
+int trajopt_begin(trajopt_handle* h, const double* d_x0, const double* d_us_init, int us_mode, void* stream);
+/* run up to n_iters more iterations; *n_active_out (may be NULL) = problems still running afterwards */
+int trajopt_iterate(trajopt_handle* h, int n_iters, int* n_active_out, void* stream);
+/* any output pointer may be NULL.  d_xs [B][N+1][NS], d_us [B][N][NU], per-problem arrays [B] */
+int trajopt_export(trajopt_handle* h, double* d_xs, double* d_us, double* d_J, int32_t* d_iters,
+                   int32_t* d_status, double* d_grad, double* d_defect, void* stream);
+/* histories, problem-major: d_J_hist [B][max_iters], d_grad_hist [B][max_iters+1],
+ * d_defect_hist [B][max_iters+1], d_alpha_hist [B][max_iters] (accepted step index, -1 none) */
+int trajopt_export_hist(trajopt_handle* h, double* d_J_hist, double* d_grad_hist, double* d_defect_hist,
+                        int32_t* d_alpha_hist, void* stream);
+/* AL only: d_lmbd [B][N+1][2NU], d_imu [B][N+1][2NU] (diagonal), d_mu [B], d_outer_iters [B], d_violation [B] */
+int trajopt_export_al(trajopt_handle* h, double* d_lmbd, double* d_imu, double* d_mu, int32_t* d_outer_iters,
+                      double* d_violation, void* stream);
+
+/* begin + iterate(max_iters) + export */
+int trajopt_solve(trajopt_handle* h, const double* d_x0, const double* d_us_init, int us_mode,
+                  double* d_xs, double* d_us, double* d_J, int32_t* d_iters, int32_t* d_status,
+                  double* d_grad, double* d_defect, void* stream);
+/* same with HOST buffers (pinned for full speed): copies in, solves, copies out, synchronises */
+int trajopt_solve_host(trajopt_handle* h, const double* h_x0, const double* h_us_init, int us_mode,
+                       double* h_xs, double* h_us, double* h_J, int32_t* h_iters, int32_t* h_status,
+                       double* h_grad, double* h_defect, void* stream);
+
+/* ---- parity-test exports (dense, problem-major) ------------------------------------------- */
+/* linearise the CURRENT trajectory: d_Fx [B][N][NX][NX], d_Fu [B][N][NX][NU], d_defect [B][N][NX],
+ * d_L [B][N+1], d_Lx [B][N+1][NX], d_Lxx [B][N+1][NX][NX], d_Lu [B][N][NU]; any may be NULL */
+int trajopt_debug_linearize(trajopt_handle* h, double* d_Fx, double* d_Fu, double* d_defect, double* d_L,
+                            double* d_Lx, double* d_Lxx, double* d_Lu, void* stream);
+/* gains of the last backward pass: d_k [B][N][NU], d_K [B][N][NU][NX] */
+int trajopt_debug_gains(trajopt_handle* h, double* d_k, double* d_K, void* stream);
+/* Lie-group primitives on n independent inputs (problem-major rows), see csrc/api.cu for op codes */
+int trajopt_debug_lie(int op, int n, const double* d_in, double* d_out, void* stream);
+
+/* kernels launched by this library since the last reset (for bench.py's gpu_launches claim) */
+int64_t trajopt_launch_count(int reset);
+/* device seconds spent in the phases of the last trajopt_iterate calls since reset:
+ * out[0]=linearise, out[1]=backward, out[2]=forward, out[3]=other; and their launch counts in cnt[4] */
+int trajopt_phase_times(trajopt_handle* h, double* out_ms, int64_t* cnt, int reset);
+int trajopt_set_profiling(trajopt_handle* h, int enable);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRAJOPT_B200_H */

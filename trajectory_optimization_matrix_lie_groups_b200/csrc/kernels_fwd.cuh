@@ -1,0 +1,533 @@
+// Forward passes, line-search bookkeeping, augmented-Lagrangian update and layout exports.
+#pragma once
+#include "kernels.cuh"
+
+namespace trajopt {
+
+// ------------------------------------------------------------------------------------------
+// Forward rollout of one candidate step size per thread.
+//   thread t -> problem b = t % Bp, candidate a = a_lo + t / Bp
+//   MS  (:2641-2740):  dx = x_new(i) (-) x(i);  du = alpha k + K dx;  u_new = u + du
+//        nonlinear:  q_new(i+1) = q(i+1) Exp(alpha d_q) f(x,u).q^-1 f(x_new,u_new).q
+//                    xi_new(i+1) = xi(i+1) + f_new.xi - f.xi + alpha d_xi
+//        linear   :  x_new(i+1) = x(i+1) (+) (A dx + B du + alpha d)
+//   SS  (:2030-2082):  nonlinear: x_new(i+1) = f(x_new(i), u_new(i));  linear: x(i+1) (+) (A dx + B du)
+//   WRITE  : store the candidate trajectory into the problem's other buffer
+//   COST   : accumulate J_new = sum_i l(x_new_i, u_new_i) + l_N left to right (:2084-2096);
+//            MS additionally accumulates the candidate's defect norm (:2565-2566)
+// Which problems run: `need` < 0 -> every running problem; otherwise those with ls_state == need.
+// ------------------------------------------------------------------------------------------
+template <int KIND, bool MS, bool LINEAR, bool WRITE, bool COST>
+__global__ void __launch_bounds__(kBlock) k_forward(const Params prm, Work w, int a_lo, int a_cnt, int need,
+                                                    int use_ls_state_as_alpha) {
+    using D = Dims<KIND>;
+    using LR = LinRec<KIND>;
+    constexpr int NX = D::NX, NP = D::NP, NU = D::NU, NV = NX - NP, F = LR::LEN;
+    const int t = blockIdx.x * kBlock + threadIdx.x;
+    const int Bp = prm.Bp, N = prm.N;
+    const int b = t % Bp;
+    int ai = a_lo + t / Bp;
+    if (t / Bp >= a_cnt || b >= prm.B) return;
+    if (w.status[b] != TRAJOPT_RUNNING) return;
+    if (need >= -1 && w.ls_state[b] != need && !use_ls_state_as_alpha) return;
+    if (use_ls_state_as_alpha) {
+        ai = w.ls_state[b];
+        if (ai < 0) return;
+    }
+    // alpha = 1.1 ** (-ai**2)  (:1908, :2472); index 0 is exactly 1.0
+    const double alpha = (ai == 0) ? 1.0 : pow(1.1, -(double)(ai * ai));
+
+    const int cur = w.sel[b];
+    const double* X = w.X[cur];
+    const double* U = w.U[cur];
+    double* Xn = w.X[1 - cur];
+    double* Un = w.U[1 - cur];
+    const double* lin = w.lin;
+
+    State<KIND> xnew, x, xnext;
+    load_state<KIND>(X, 0, Bp, b, x);
+    xnew = x;
+    if (WRITE) store_state<KIND>(Xn, 0, Bp, b, xnew);
+    double J = 0.0, dsq = 0.0;
+
+    for (int i = 0; i < N; ++i) {
+        const double* refrow = w.ref + (size_t)i * RefRow<KIND>::N;
+        double dx[NX];
+        state_minus<KIND>(xnew, x, dx);
+        double u[NU], unew[NU], du[NU];
+#pragma unroll
+        for (int a = 0; a < NU; ++a) {
+            u[a] = U[soa(i, a, NU, Bp, b)];
+            double s = alpha * w.kff[soa(i, a, NU, Bp, b)];
+#pragma unroll
+            for (int c = 0; c < NX; ++c) s += w.Kfb[soa(i, a * NX + c, NU * NX, Bp, b)] * dx[c];
+            du[a] = s;
+            unew[a] = u[a] + s;
+        }
+        if (WRITE) {
+#pragma unroll
+            for (int a = 0; a < NU; ++a) Un[soa(i, a, NU, Bp, b)] = unew[a];
+        }
+        if (COST) {
+            double c = stage_cost<KIND>(prm, xnew, unew, refrow, false);
+            if (prm.has_constraints) {
+                double lam[2 * NU], imu[2 * NU], t1[NU], t2[NU];
+#pragma unroll
+                for (int j = 0; j < 2 * NU; ++j) {
+                    lam[j] = w.lam[soa(i, j, 2 * NU, Bp, b)];
+                    imu[j] = w.imu[soa(i, j, 2 * NU, Bp, b)];
+                }
+                c += al_terms<NU>(prm, unew, lam, imu, t1, t2);
+            }
+            J = J + c;
+        }
+        load_state<KIND>(X, i + 1, Bp, b, xnext);
+
+        State<KIND> xn1;
+        if constexpr (LINEAR) {
+            // step = A dx + B du (+ alpha d), pose part retracts x(i+1)
+            AMat<KIND> A;
+            A.load(lin, i, Bp, b);
+            double st[NX];
+#pragma unroll
+            for (int r = 0; r < NX; ++r) {
+                double s = 0.0;
+#pragma unroll
+                for (int c = 0; c < NX; ++c)
+                    if (AMat<KIND>::nz(r, c)) s += A.get(r, c) * dx[c];
+                if (r >= NP) {
+#pragma unroll
+                    for (int a = 0; a < NU; ++a)
+                        if (bv_nz<KIND>(r - NP, a)) s += prm.Bv[(r - NP) * NU + a] * du[a];
+                }
+                if constexpr (MS) s += alpha * lin[soa(i, LR::D_OFF + r, F, Bp, b)];
+                st[r] = s;
+            }
+            if constexpr (KIND == TRAJOPT_SO3) {
+                double qe[4];
+                so3_exp(st, qe);
+                quat_compose(xnext.q, qe, xn1.q);
+            } else {
+                double qe[4], pe[3];
+                se3_exp(st, qe, pe);
+                se3_compose(xnext.q, xnext.p, qe, pe, xn1.q, xn1.p);
+            }
+#pragma unroll
+            for (int j = 0; j < NV; ++j) xn1.xi[j] = xnext.xi[j] + st[NP + j];
+        } else {
+            State<KIND> fnew;
+            dyn_step<KIND>(prm, xnew, unew, fnew);
+            if constexpr (MS) {
+                State<KIND> fold;
+                dyn_step<KIND>(prm, x, u, fold);
+                double d[NX];
+#pragma unroll
+                for (int j = 0; j < NX; ++j) d[j] = alpha * lin[soa(i, LR::D_OFF + j, F, Bp, b)];
+                if constexpr (KIND == TRAJOPT_SO3) {
+                    double qe[4], q1[4], q2[4];
+                    so3_exp(d, qe);
+                    quat_compose(xnext.q, qe, q1);
+                    quat_compose_inv_r(q1, fold.q, q2);
+                    quat_compose(q2, fnew.q, xn1.q);
+                } else {
+                    double qe[4], pe[3], q1[4], p1[3], q2[4], p2[3];
+                    se3_exp(d, qe, pe);
+                    se3_compose(xnext.q, xnext.p, qe, pe, q1, p1);
+                    se3_compose_inv_r(q1, p1, fold.q, fold.p, q2, p2);
+                    se3_compose(q2, p2, fnew.q, fnew.p, xn1.q, xn1.p);
+                }
+#pragma unroll
+                for (int j = 0; j < NV; ++j) xn1.xi[j] = xnext.xi[j] + fnew.xi[j] - fold.xi[j] + d[NP + j];
+            } else {
+                xn1 = fnew;
+            }
+        }
+        if (MS && COST) {
+            // defect of the candidate: f(x_new_i, u_new_i) (-) x_new(i+1)   (:2790-2810)
+            State<KIND> fnew;
+            dyn_step<KIND>(prm, xnew, unew, fnew);
+            double dd[NX];
+            defect<KIND>(fnew, xn1, dd);
+#pragma unroll
+            for (int j = 0; j < NX; ++j) dsq += dd[j] * dd[j];
+        }
+        if (WRITE) store_state<KIND>(Xn, i + 1, Bp, b, xn1);
+        xnew = xn1;
+        x = xnext;
+    }
+    if (COST) {
+        const double* refrow = w.ref + (size_t)N * RefRow<KIND>::N;
+        J = J + stage_cost<KIND>(prm, xnew, nullptr, refrow, true);
+        w.Jcand[(size_t)ai * Bp + b] = J;
+        if (MS) w.Jcand[(size_t)(prm.n_alphas + ai) * Bp + b] = sqrt(dsq);
+    }
+}
+
+// MS without line search: alpha = 1 is always accepted (:2592-2600)
+__global__ void k_accept_all(const Params prm, Work w, int it) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= prm.B || w.status[b] != TRAJOPT_RUNNING) return;
+    w.sel[b] = 1 - w.sel[b];
+    w.alphahist[(size_t)it * prm.Bp + b] = 0;
+    w.iters[b] = it + 1;
+}
+
+// count problems that are still running into counters[0]
+__global__ void k_count_running(const Params prm, Work w) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool run = (b < prm.B) && (w.status[b] == TRAJOPT_RUNNING);
+    const unsigned m = __ballot_sync(0xffffffffu, run);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(&w.counters[0], __popc(m));
+}
+
+// SS line search (:1972-1990): examine candidates [a_lo, a_lo+a_cnt) in index order, accept the
+// first J_new < J_opt.  first pass (a_lo == 0): the accepted trajectory is already in the other
+// buffer; later passes only pick the index and a final k_forward<WRITE> materialises it.
+__global__ void k_ls_select_ss(const Params prm, Work w, int it, int a_lo, int a_cnt, int last) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in = (b < prm.B) && (w.status[b] == TRAJOPT_RUNNING);
+    bool pending = false;
+    if (in && (a_lo == 0 || w.ls_state[b] == -1)) {
+        const double Jopt = w.J[b];
+        int found = -1;
+        for (int a = a_lo; a < a_lo + a_cnt; ++a) {
+            if (w.Jcand[(size_t)a * prm.Bp + b] < Jopt) { found = a; break; }
+        }
+        if (found >= 0) {
+            w.ls_state[b] = found;
+        } else if (!last) {
+            w.ls_state[b] = -1;
+            pending = true;
+        } else {
+            // "Couldn't find descent direction" (:2005-2007): J_hist gets J_opt, solve stops
+            w.ls_state[b] = -2;
+            w.Jhist[(size_t)it * prm.Bp + b] = Jopt;
+            w.alphahist[(size_t)it * prm.Bp + b] = -1;
+            w.iters[b] = it + 1;
+            w.status[b] = TRAJOPT_NO_DESCENT;
+        }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, pending);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(&w.counters[1], __popc(m));
+}
+
+// commit an accepted SS candidate whose trajectory is in the other buffer
+__global__ void k_ls_commit_ss(const Params prm, Work w, int it) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= prm.B || w.status[b] != TRAJOPT_RUNNING) return;
+    const int a = w.ls_state[b];
+    if (a < 0) return;
+    const double Jn = w.Jcand[(size_t)a * prm.Bp + b];
+    w.sel[b] = 1 - w.sel[b];
+    w.J[b] = Jn;
+    w.Jhist[(size_t)it * prm.Bp + b] = Jn;
+    w.alphahist[(size_t)it * prm.Bp + b] = a;
+    w.iters[b] = it + 1;
+    w.ls_state[b] = -2;
+    if (it + 1 >= prm.max_iters) w.status[b] = TRAJOPT_MAX_ITER;
+}
+
+// ------------------------------------------------------------------------------------------
+// MS merit line search (:2549-2590).  k_ms_expected: linear rollout with alpha = 1 for the
+// expected cost change (c1, c2) (:2756-2769) and the defect weight (:2774-2788); stored in
+// Jcand rows [2 n_alphas .. 2 n_alphas + 3] = c1, c2, d_weight, merit.
+// ------------------------------------------------------------------------------------------
+template <int KIND>
+__global__ void __launch_bounds__(kBlock) k_ms_expected(const Params prm, Work w, double* dweight_prev) {
+    using D = Dims<KIND>;
+    using LR = LinRec<KIND>;
+    constexpr int NX = D::NX, NP = D::NP, NU = D::NU, NV = NX - NP, F = LR::LEN;
+    const int b = blockIdx.x * kBlock + threadIdx.x;
+    const int Bp = prm.Bp, N = prm.N;
+    if (b >= prm.B || w.status[b] != TRAJOPT_RUNNING) return;
+    const double* lin = w.lin;
+    const int cur = w.sel[b];
+    const double* U = w.U[cur];
+    (void)U;
+    // In the linear rollout the state error obeys dx(i+1) = A dx + B du + d exactly in the
+    // tangent of x(i+1):  x_new(i+1) = x(i+1) (+) step  =>  x_new(i+1) (-) x(i+1) = Log(Exp(step)).
+    // The reference evaluates Log(Exp(.)) numerically through manif; so do we.
+    double dx[NX];
+#pragma unroll
+    for (int j = 0; j < NX; ++j) dx[j] = 0.0;
+    double c1 = 0.0, c2 = 0.0;
+    for (int i = 0; i < N; ++i) {
+        double du[NU];
+#pragma unroll
+        for (int a = 0; a < NU; ++a) {
+            double s = w.kff[soa(i, a, NU, Bp, b)];
+#pragma unroll
+            for (int c = 0; c < NX; ++c) s += w.Kfb[soa(i, a * NX + c, NU * NX, Bp, b)] * dx[c];
+            du[a] = s;
+        }
+        // first / second order terms
+        double f1 = 0.0, f2 = 0.0;
+#pragma unroll
+        for (int c = 0; c < NX; ++c) f1 += lin[soa(i, LR::LX_OFF + c, F, Bp, b)] * dx[c];
+#pragma unroll
+        for (int a = 0; a < NU; ++a) f1 += lin[soa(i, LR::LU_OFF + a, F, Bp, b)] * du[a];
+        // dx^T l_xx dx
+#pragma unroll
+        for (int r = 0; r < NP; ++r)
+#pragma unroll
+            for (int c = 0; c < NP; ++c)
+                f2 += dx[r] * lin[soa(i, LR::LXX_OFF + sym_idx(NP, r, c), F, Bp, b)] * dx[c];
+#pragma unroll
+        for (int r = 0; r < NV; ++r)
+#pragma unroll
+            for (int c = 0; c < NV; ++c) f2 += dx[NP + r] * 2.0 * prm.W2[r * NV + c] * dx[NP + c];
+        // du^T l_uu du  (l_ux = 0)
+#pragma unroll
+        for (int r = 0; r < NU; ++r)
+#pragma unroll
+            for (int c = 0; c < NU; ++c) {
+                double l = 2.0 * prm.R[r * NU + c];
+                if (r == c) l += lin[soa(i, LR::LUU_OFF + r, F, Bp, b)];
+                f2 += du[r] * l * du[c];
+            }
+        c1 += f1;
+        c2 += f2;
+        // propagate
+        AMat<KIND> A;
+        A.load(lin, i, Bp, b);
+        double st[NX];
+#pragma unroll
+        for (int r = 0; r < NX; ++r) {
+            double s = lin[soa(i, LR::D_OFF + r, F, Bp, b)];
+#pragma unroll
+            for (int c = 0; c < NX; ++c)
+                if (AMat<KIND>::nz(r, c)) s += A.get(r, c) * dx[c];
+            if (r >= NP) {
+#pragma unroll
+                for (int a = 0; a < NU; ++a)
+                    if (bv_nz<KIND>(r - NP, a)) s += prm.Bv[(r - NP) * NU + a] * du[a];
+            }
+            st[r] = s;
+        }
+        // pose part goes through Exp then Log (rminus of the retracted pose against the node)
+        if constexpr (KIND == TRAJOPT_SO3) {
+            double qe[4];
+            so3_exp(st, qe);
+            so3_log(qe, dx);
+        } else {
+            double qe[4], pe[3];
+            se3_exp(st, qe, pe);
+            se3_log(qe, pe, dx);
+        }
+#pragma unroll
+        for (int j = NP; j < NX; ++j) dx[j] = st[j];
+    }
+    {
+        double f1 = 0.0, f2 = 0.0;
+#pragma unroll
+        for (int c = 0; c < NX; ++c) f1 += lin[soa(N, LR::LX_OFF + c, F, Bp, b)] * dx[c];
+#pragma unroll
+        for (int r = 0; r < NP; ++r)
+#pragma unroll
+            for (int c = 0; c < NP; ++c)
+                f2 += dx[r] * lin[soa(N, LR::LXX_OFF + sym_idx(NP, r, c), F, Bp, b)] * dx[c];
+#pragma unroll
+        for (int r = 0; r < NV; ++r)
+#pragma unroll
+            for (int c = 0; c < NV; ++c) f2 += dx[NP + r] * 2.0 * prm.P2[r * NV + c] * dx[NP + c];
+        c1 += f1;
+        c2 += f2;
+    }
+    const double dn = w.dnorm[b];
+    double dw;
+    if (dn < prm.defect_kappa) dw = dweight_prev[b];
+    else dw = fmax(prm.defect_mu0, prm.defect_mu0 + fabs(c1 + 0.5 * c2) / ((1.0 - prm.defect_rho) * dn));
+    dweight_prev[b] = dw;
+    const size_t base = (size_t)(2 * prm.n_alphas) * Bp + b;
+    w.Jcand[base] = c1;
+    w.Jcand[base + Bp] = c2;
+    w.Jcand[base + 2 * (size_t)Bp] = dw;
+    // merit uses J_opt = L.sum() (pairwise, :2507) of the current trajectory
+    w.Jcand[base + 3 * (size_t)Bp] = pairwise_sum(w.Lc + b, (size_t)Bp, N + 1) + dw * dn;
+}
+
+// accept the first alpha with merit_new - merit < gamma (dJ_exp(alpha) - alpha w ||d||) (:2576)
+__global__ void k_ls_select_ms(const Params prm, Work w, int it, int a_lo, int a_cnt, int last) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in = (b < prm.B) && (w.status[b] == TRAJOPT_RUNNING);
+    bool pending = false;
+    const int Bp = prm.Bp;
+    if (in && (a_lo == 0 || w.ls_state[b] == -1)) {
+        const size_t base = (size_t)(2 * prm.n_alphas) * Bp + b;
+        const double c1 = w.Jcand[base], c2 = w.Jcand[base + Bp], dw = w.Jcand[base + 2 * (size_t)Bp];
+        const double merit = w.Jcand[base + 3 * (size_t)Bp];
+        const double dn = w.dnorm[b];
+        int found = -1;
+        for (int a = a_lo; a < a_lo + a_cnt; ++a) {
+            const double alpha = (a == 0) ? 1.0 : pow(1.1, -(double)(a * a));
+            const double Jn = w.Jcand[(size_t)a * Bp + b];
+            const double dnn = w.Jcand[(size_t)(prm.n_alphas + a) * Bp + b];
+            const double merit_new = Jn + dw * dnn;
+            const double Jexp = alpha * c1 + 0.5 * (alpha * alpha) * c2;
+            if (merit_new - merit < prm.defect_gamma * (Jexp - alpha * dw * dn)) { found = a; break; }
+        }
+        if (found >= 0) {
+            w.ls_state[b] = found;
+        } else if (!last) {
+            w.ls_state[b] = -1;
+            pending = true;
+        } else {
+            w.ls_state[b] = -2;
+            w.alphahist[(size_t)it * Bp + b] = -1;
+            w.iters[b] = it + 1;
+            w.status[b] = TRAJOPT_NO_DESCENT;
+            // the callback still records J_opt (pairwise sum of the unchanged trajectory) (:2621-2626)
+            w.Jhist[(size_t)it * Bp + b] = merit - dw * dn;
+        }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, pending);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(&w.counters[1], __popc(m));
+}
+
+__global__ void k_ls_commit_ms(const Params prm, Work w, int it) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= prm.B || w.status[b] != TRAJOPT_RUNNING) return;
+    const int a = w.ls_state[b];
+    if (a < 0) return;
+    w.sel[b] = 1 - w.sel[b];
+    w.alphahist[(size_t)it * prm.Bp + b] = a;
+    w.iters[b] = it + 1;
+    w.ls_state[b] = -2;
+}
+
+// ------------------------------------------------------------------------------------------
+// Augmented Lagrangian outer update (:3242-3290) for InputConstraint g = [lb - u; u - ub]
+// ------------------------------------------------------------------------------------------
+template <int KIND>
+__global__ void k_al_update(const Params prm, Work w, double tol_constr, double mu_scale, double mu_max, int outer_it) {
+    constexpr int NU = Dims<KIND>::NU;
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const int Bp = prm.Bp, N = prm.N;
+    bool notdone = false;
+    if (b < prm.B && !w.al_done[b]) {
+        const double* U = w.U[w.sel[b]];
+        // max over stages of g (terminal row is zeros, :3245-3247)
+        double gmax = 0.0;
+        for (int i = 0; i < N; ++i) {
+#pragma unroll
+            for (int j = 0; j < NU; ++j) {
+                const double u = U[soa(i, j, NU, Bp, b)];
+                gmax = fmax(gmax, fmax(prm.lb[j] - u, u - prm.ub[j]));
+            }
+        }
+        w.al_viol[b] = gmax;
+        w.al_outer[b] = outer_it + 1;
+        if (gmax < tol_constr) {
+            w.al_done[b] = 1;
+        } else {
+            notdone = true;
+            const double mu_new = fmin(w.al_mu[b] * mu_scale, mu_max);
+            for (int i = 0; i < N; ++i) {
+#pragma unroll
+                for (int j = 0; j < NU; ++j) {
+                    const double u = U[soa(i, j, NU, Bp, b)];
+                    const double g[2] = {prm.lb[j] - u, u - prm.ub[j]};
+#pragma unroll
+                    for (int s = 0; s < 2; ++s) {
+                        const size_t idx = soa(i, s * NU + j, 2 * NU, Bp, b);
+                        const double ln = fmax(0.0, w.lam[idx] + w.imu[idx] * g[s]);
+                        w.lam[idx] = ln;
+                        w.imu[idx] = (g[s] < 0.0 && ln == 0.0) ? 0.0 : mu_new;
+                    }
+                }
+            }
+            // terminal row: g = 0 -> lambda stays 0, Imu = mu_new (no effect on the cost)
+#pragma unroll
+            for (int j = 0; j < 2 * NU; ++j) w.imu[soa(N, j, 2 * NU, Bp, b)] = mu_new;
+            w.al_mu[b] = mu_new;
+        }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, notdone);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(&w.counters[2], __popc(m));
+}
+
+template <int KIND>
+__global__ void k_al_init(const Params prm, Work w, double mu0) {
+    constexpr int NU = Dims<KIND>::NU;
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const int stage = blockIdx.y;
+    if (b >= prm.Bp) return;
+#pragma unroll
+    for (int j = 0; j < 2 * NU; ++j) {
+        w.lam[soa(stage, j, 2 * NU, prm.Bp, b)] = 0.0;
+        w.imu[soa(stage, j, 2 * NU, prm.Bp, b)] = mu0;
+    }
+    if (stage == 0) {
+        w.al_mu[b] = mu0;
+        w.al_outer[b] = 0;
+        w.al_viol[b] = 0.0;
+        w.al_done[b] = (b < prm.B) ? 0 : 1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Layout exports: SoA [stage][field][Bp] -> problem-major
+// ------------------------------------------------------------------------------------------
+// out[b][stage][f] = src_sel[b][stage][f][b]   (grid.y = stage)
+__global__ void k_export_traj(int B, int Bp, int F, const double* s0, const double* s1, const int* sel, double* out, int nstage) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const int stage = blockIdx.y;
+    if (b >= B) return;
+    const double* src = (sel && sel[b]) ? s1 : s0;
+    for (int f = 0; f < F; ++f) out[((size_t)b * nstage + stage) * F + f] = src[((size_t)stage * F + f) * Bp + b];
+}
+// out[b][row] = src[row][b]
+template <typename T>
+__global__ void k_export_rows(int B, int Bp, int rows, const T* src, T* out) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (b >= B) return;
+    out[(size_t)b * rows + r] = src[(size_t)r * Bp + b];
+}
+
+// dense linearisation for parity tests
+template <int KIND>
+__global__ void k_export_lin(const Params prm, Work w, double* Fx, double* Fu, double* dd, double* L, double* Lx, double* Lxx, double* Lu) {
+    using D = Dims<KIND>;
+    using LR = LinRec<KIND>;
+    constexpr int NX = D::NX, NP = D::NP, NU = D::NU, NV = NX - NP, F = LR::LEN;
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y;
+    const int Bp = prm.Bp, N = prm.N;
+    if (b >= prm.B) return;
+    const double* lin = w.lin;
+    if (L) L[(size_t)b * (N + 1) + i] = w.Lc[(size_t)i * Bp + b];
+    if (Lx)
+        for (int c = 0; c < NX; ++c) Lx[((size_t)b * (N + 1) + i) * NX + c] = lin[soa(i, LR::LX_OFF + c, F, Bp, b)];
+    if (Lxx) {
+        const double* W2 = (i == N) ? prm.P2 : prm.W2;
+        for (int r = 0; r < NX; ++r)
+            for (int c = 0; c < NX; ++c) {
+                double v = 0.0;
+                if (r < NP && c < NP) v = lin[soa(i, LR::LXX_OFF + sym_idx(NP, r, c), F, Bp, b)];
+                else if (r >= NP && c >= NP) v = 2.0 * W2[(r - NP) * NV + (c - NP)];
+                Lxx[(((size_t)b * (N + 1) + i) * NX + r) * NX + c] = v;
+            }
+    }
+    if (i == N) return;
+    AMat<KIND> A;
+    A.load(lin, i, Bp, b);
+    if (Fx) {
+#pragma unroll
+        for (int r = 0; r < NX; ++r)
+#pragma unroll
+            for (int c = 0; c < NX; ++c)
+                Fx[(((size_t)b * N + i) * NX + r) * NX + c] = AMat<KIND>::nz(r, c) ? A.get(r, c) : 0.0;
+    }
+    if (Fu) {
+        for (int r = 0; r < NX; ++r)
+            for (int a = 0; a < NU; ++a)
+                Fu[(((size_t)b * N + i) * NX + r) * NU + a] = (r >= NP && bv_nz<KIND>(r - NP, a)) ? prm.Bv[(r - NP) * NU + a] : 0.0;
+    }
+    if (dd)
+        for (int c = 0; c < NX; ++c) dd[((size_t)b * N + i) * NX + c] = lin[soa(i, LR::D_OFF + c, F, Bp, b)];
+    if (Lu)
+        for (int a = 0; a < NU; ++a) Lu[((size_t)b * N + i) * NU + a] = lin[soa(i, LR::LU_OFF + a, F, Bp, b)];
+}
+
+}  // namespace trajopt
