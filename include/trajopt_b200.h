@@ -109,6 +109,9 @@ int trajopt_export(trajopt_handle* h, double* d_xs, double* d_us, double* d_J, i
  * d_defect_hist [B][max_iters+1], d_alpha_hist [B][max_iters] (accepted step index, -1 none) */
 int trajopt_export_hist(trajopt_handle* h, double* d_J_hist, double* d_grad_hist, double* d_defect_hist,
                         int32_t* d_alpha_hist, void* stream);
+/* regulariser state after the last backward pass: d_mu [B], d_delta [B] (traopt_controller.py:1899-1900,
+ * 2233-2246; `mu` is what the on_iteration callbacks receive) */
+int trajopt_export_reg(trajopt_handle* h, double* d_mu, double* d_delta, void* stream);
 /* AL only: d_lmbd [B][N+1][2NU], d_imu [B][N+1][2NU] (diagonal), d_mu [B], d_outer_iters [B], d_violation [B] */
 int trajopt_export_al(trajopt_handle* h, double* d_lmbd, double* d_imu, double* d_mu, int32_t* d_outer_iters,
                       double* d_violation, void* stream);

@@ -353,28 +353,57 @@ __global__ void __launch_bounds__(128) k_linearize(const Params prm, Work w) {
 // NumPy pairwise summation (numpy/_core/src/umath/loops_utils.h.src, DOUBLE_pairwise_sum) over a
 // strided column: the reference's J_opt = L.sum() (traopt_controller.py:1935).
 // ------------------------------------------------------------------------------------------
-__device__ inline double pairwise_sum(const double* a, size_t stride, int n) {
+__device__ inline double pairwise_leaf(const double* a, size_t stride, int n) {   // n <= 128
     if (n < 8) {
         double res = 0.0;
         for (int i = 0; i < n; ++i) res += a[i * stride];
         return res;
-    } else if (n <= 128) {
-        double r[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) r[j] = a[j * stride];
-        int i;
-        for (i = 8; i < n - (n % 8); i += 8) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) r[j] += a[(i + j) * stride];
-        }
-        double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
-        for (; i < n; ++i) res += a[i * stride];
-        return res;
-    } else {
-        int n2 = n / 2;
-        n2 -= n2 % 8;
-        return pairwise_sum(a, stride, n2) + pairwise_sum(a + (size_t)n2 * stride, stride, n - n2);
     }
+    double r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = a[j * stride];
+    int i;
+    for (i = 8; i < n - (n % 8); i += 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] += a[(i + j) * stride];
+    }
+    double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+    for (; i < n; ++i) res += a[i * stride];
+    return res;
+}
+// the recursion `sum(a[:n2]) + sum(a[n2:])`, n2 = n/2 rounded down to a multiple of 8, unrolled
+// onto an explicit stack (device recursion would leave the kernel's stack size undetermined)
+__device__ inline double pairwise_sum(const double* a, size_t stride, int n) {
+    if (n <= 128) return pairwise_leaf(a, stride, n);
+    int start[12], len[12], state[12];
+    double left[12];
+    int sp = 1;
+    start[0] = 0; len[0] = n; state[0] = 0;
+    double ret = 0.0;
+    while (sp > 0) {
+        const int t = sp - 1;
+        if (len[t] <= 128) {
+            ret = pairwise_leaf(a + (size_t)start[t] * stride, stride, len[t]);
+            --sp;
+            continue;
+        }
+        int n2 = len[t] / 2;
+        n2 -= n2 % 8;
+        if (state[t] == 0) {
+            state[t] = 1;
+            start[sp] = start[t]; len[sp] = n2; state[sp] = 0;
+            ++sp;
+        } else if (state[t] == 1) {
+            left[t] = ret;
+            state[t] = 2;
+            start[sp] = start[t] + n2; len[sp] = len[t] - n2; state[sp] = 0;
+            ++sp;
+        } else {
+            ret = left[t] + ret;
+            --sp;
+        }
+    }
+    return ret;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(kBlock) k_forward(const Params prm, Work w, in
     if (need >= -1 && w.ls_state[b] != need && !use_ls_state_as_alpha) return;
     if (use_ls_state_as_alpha) {
         ai = w.ls_state[b];
-        if (ai < 0) return;
+        if (ai < a_lo) return;       // a_lo = 1: step size 0 was already written by the first pass
     }
     // alpha = 1.1 ** (-ai**2)  (:1908, :2472); index 0 is exactly 1.0
     const double alpha = (ai == 0) ? 1.0 : pow(1.1, -(double)(ai * ai));

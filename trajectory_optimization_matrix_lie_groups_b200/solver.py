@@ -1,0 +1,246 @@
+"""`BatchSolver`: the one Python object that owns a native solver handle.
+
+Everything numeric happens in `libtrajopt_b200.so` (hand-written sm_100a CUDA behind the C ABI of
+include/trajopt_b200.h); PyTorch is used here only for device memory and streams.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import lib, check
+
+KINDS = {"so3": _lib.SO3, "se3": _lib.SE3, "drone": _lib.DRONE}
+METHODS = {"ss": _lib.SS, "ms": _lib.MS, "al_ms": _lib.AL_MS}
+DIMS = {  # kind -> (NX, NP, NU, NS)
+    "so3": (6, 3, 3, 7), "se3": (12, 6, 6, 13), "drone": (12, 6, 4, 13),
+}
+
+
+def _ptr(t):
+    return C.c_void_p(0) if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class BatchSolver:
+    """B independent tracking problems of one family, solved together on one GPU.
+
+    kind: 'so3' | 'se3' | 'drone';  method: 'ss' | 'ms' | 'al_ms'.
+    """
+
+    def __init__(self, kind, method, N, B, device=None):
+        if not torch.cuda.is_available():
+            raise _lib.TrajoptError("no CUDA device: this solver has no CPU path")
+        self.kind, self.method, self.N, self.B = kind, method, int(N), int(B)
+        self.NX, self.NP, self.NU, self.NS = DIMS[kind]
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        self.device = dev
+        torch.cuda.init()
+        torch.zeros(1, device=dev)          # make sure torch's primary context exists on the device
+        h = C.c_void_p()
+        check(lib.trajopt_create(KINDS[kind], METHODS[method], self.N, self.B, dev.index, C.byref(h)))
+        self._h = h
+        self.max_iters = None
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.trajopt_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------------------ configuration
+    def set_params(self, *, dt, Ib, mass, Q, R, P, gravity=9.8, max_iters=100, tol_grad_norm=1e-6,
+                   tol_d_norm=1e-6, max_reg=1e10, rollout="nonlinear", line_search=False, n_alphas=0,
+                   defect_kappa=0.0, lb=None, ub=None, n_al_iters=100, al_mu0=1e-2, al_mu_scale=10.0,
+                   al_mu_max=1e8, tol_constr=1e-2):
+        NX, NU = self.NX, self.NU
+        p = _lib.Params()
+        p.dt = float(dt)
+        p.Ib[:] = np.asarray(Ib, dtype=np.float64).reshape(9).tolist()
+        p.mass = float(mass)
+        p.gravity = float(gravity)
+        for name, M, n in (("Q", Q, NX), ("P", P, NX), ("R", R, NU)):
+            M = np.asarray(M, dtype=np.float64)
+            if M.shape != (n, n):
+                raise ValueError(f"{name} must be {n}x{n}")
+            buf = getattr(p, name)
+            flat = M.reshape(-1)
+            for i in range(flat.size):
+                buf[i] = flat[i]
+        p.has_constraints = int(lb is not None)
+        if lb is not None:
+            lb = np.broadcast_to(np.asarray(lb, dtype=np.float64), (NU,))
+            ub = np.broadcast_to(np.asarray(ub, dtype=np.float64), (NU,))
+            for i in range(NU):
+                p.lb[i], p.ub[i] = lb[i], ub[i]
+        if rollout not in ("linear", "nonlinear"):
+            raise ValueError("rollout must be 'linear' or 'nonlinear'")
+        p.rollout_linear = int(rollout == "linear")
+        p.line_search = int(bool(line_search))
+        p.n_alphas = int(n_alphas)
+        p.max_iters = int(max_iters)
+        p.tol_grad_norm = float(tol_grad_norm)
+        p.tol_d_norm = float(tol_d_norm)
+        p.max_reg = float(max_reg) if max_reg else 0.0
+        p.defect_kappa = float(defect_kappa)
+        p.n_al_iters = int(n_al_iters)
+        p.al_mu0, p.al_mu_scale, p.al_mu_max, p.tol_constr = float(al_mu0), float(al_mu_scale), float(al_mu_max), float(tol_constr)
+        check(lib.trajopt_set_params(self._h, C.byref(p)))
+        self.max_iters = int(max_iters)
+        self.n_al_iters = int(n_al_iters)
+
+    def set_reference(self, q_ref_rows, xi_ref):
+        """q_ref_rows: (N+1, 7|4) quat[+pos] rows; xi_ref: (N+1, 6|3).  Shared by the whole batch."""
+        q = np.ascontiguousarray(q_ref_rows, dtype=np.float64)
+        xi = np.ascontiguousarray(xi_ref, dtype=np.float64)
+        if q.shape != (self.N + 1, self.NS - (self.NX - self.NP)) or xi.shape != (self.N + 1, self.NX - self.NP):
+            raise ValueError(f"reference shapes {q.shape}, {xi.shape} do not match N={self.N}, kind={self.kind}")
+        check(lib.trajopt_set_reference(self._h, q.ctypes.data_as(C.c_void_p), xi.ctypes.data_as(C.c_void_p)))
+
+    # ------------------------------------------------------------------------------------ solving
+    def _dev(self, a, shape=None, dtype=torch.float64):
+        t = torch.as_tensor(a, dtype=dtype)
+        if t.device != self.device:
+            t = t.to(self.device)
+        t = t.contiguous()
+        if shape is not None and tuple(t.shape) != tuple(shape):
+            raise ValueError(f"expected shape {tuple(shape)}, got {tuple(t.shape)}")
+        return t
+
+    def _us_arg(self, us_init):
+        if us_init is None:
+            return None, 0
+        us = torch.as_tensor(us_init, dtype=torch.float64)
+        if us.dim() == 2:
+            return self._dev(us, (self.N, self.NU)), 1
+        return self._dev(us, (self.B, self.N, self.NU)), 2
+
+    def begin(self, x0, us_init=None):
+        x0 = self._dev(x0, (self.B, self.NS))
+        us, mode = self._us_arg(us_init)
+        self._keep = [x0, us]               # the library reads us_init lazily; keep it alive
+        check(lib.trajopt_begin(self._h, _ptr(x0), _ptr(us), mode, _stream(self.device)))
+
+    def iterate(self, n_iters):
+        act = C.c_int(0)
+        check(lib.trajopt_iterate(self._h, int(n_iters), C.byref(act), _stream(self.device)))
+        return act.value
+
+    def _new(self, *shape, dtype=torch.float64):
+        return torch.empty(*shape, dtype=dtype, device=self.device)
+
+    def export(self, trajectories=True):
+        B, N = self.B, self.N
+        out = {
+            "J": self._new(B), "iters": self._new(B, dtype=torch.int32), "status": self._new(B, dtype=torch.int32),
+            "grad": self._new(B), "defect": self._new(B),
+            "xs": self._new(B, N + 1, self.NS) if trajectories else None,
+            "us": self._new(B, N, self.NU) if trajectories else None,
+        }
+        check(lib.trajopt_export(self._h, _ptr(out["xs"]), _ptr(out["us"]), _ptr(out["J"]), _ptr(out["iters"]),
+                                 _ptr(out["status"]), _ptr(out["grad"]), _ptr(out["defect"]), _stream(self.device)))
+        return out
+
+    def export_hist(self):
+        B, M = self.B, self.max_iters
+        out = {"J_hist": self._new(B, M), "grad_hist": self._new(B, M + 1), "defect_hist": self._new(B, M + 1),
+               "alpha_hist": self._new(B, M, dtype=torch.int32)}
+        check(lib.trajopt_export_hist(self._h, _ptr(out["J_hist"]), _ptr(out["grad_hist"]), _ptr(out["defect_hist"]),
+                                      _ptr(out["alpha_hist"]), _stream(self.device)))
+        return out
+
+    def export_reg(self):
+        mu, delta = self._new(self.B), self._new(self.B)
+        check(lib.trajopt_export_reg(self._h, _ptr(mu), _ptr(delta), _stream(self.device)))
+        return mu, delta
+
+    def export_al(self):
+        B, N, c = self.B, self.N, 2 * self.NU
+        out = {"lmbd": self._new(B, N + 1, c), "imu": self._new(B, N + 1, c), "mu": self._new(B),
+               "outer_iters": self._new(B, dtype=torch.int32), "violation": self._new(B)}
+        check(lib.trajopt_export_al(self._h, _ptr(out["lmbd"]), _ptr(out["imu"]), _ptr(out["mu"]),
+                                    _ptr(out["outer_iters"]), _ptr(out["violation"]), _stream(self.device)))
+        return out
+
+    def solve(self, x0, us_init=None, trajectories=True):
+        """One whole fit() for every problem; inputs/outputs are device tensors."""
+        self.begin(x0, us_init)
+        units = self.n_al_iters if self.method == "al_ms" else self.max_iters + 1
+        self.iterate(units)
+        return self.export(trajectories)
+
+    def solve_host(self, x0, us_init=None, trajectories=True, out=None):
+        """Same through HOST buffers (NumPy, ideally pinned): H2D, solve, D2H inside one call."""
+        B, N = self.B, self.N
+        x0 = np.ascontiguousarray(x0, dtype=np.float64)
+        if x0.shape != (B, self.NS):
+            raise ValueError(f"x0 must be {(B, self.NS)}")
+        mode, us_p = 0, C.c_void_p(0)
+        if us_init is not None:
+            us_init = np.ascontiguousarray(us_init, dtype=np.float64)
+            mode = 1 if us_init.ndim == 2 else 2
+            us_p = us_init.ctypes.data_as(C.c_void_p)
+        if out is None:
+            out = {"J": np.empty(B), "iters": np.empty(B, dtype=np.int32), "status": np.empty(B, dtype=np.int32),
+                   "grad": np.empty(B), "defect": np.empty(B),
+                   "xs": np.empty((B, N + 1, self.NS)) if trajectories else None,
+                   "us": np.empty((B, N, self.NU)) if trajectories else None}
+
+        def hp(a):
+            return C.c_void_p(0) if a is None else a.ctypes.data_as(C.c_void_p)
+        check(lib.trajopt_solve_host(self._h, x0.ctypes.data_as(C.c_void_p), us_p, mode, hp(out["xs"]), hp(out["us"]),
+                                     hp(out["J"]), hp(out["iters"]), hp(out["status"]), hp(out["grad"]),
+                                     hp(out["defect"]), _stream(self.device)))
+        return out
+
+    # ---------------------------------------------------------------------------- parity exports
+    def debug_linearize(self):
+        B, N, NX, NU = self.B, self.N, self.NX, self.NU
+        out = {"F_x": self._new(B, N, NX, NX), "F_u": self._new(B, N, NX, NU), "d": self._new(B, N, NX),
+               "L": self._new(B, N + 1), "L_x": self._new(B, N + 1, NX), "L_xx": self._new(B, N + 1, NX, NX),
+               "L_u": self._new(B, N, NU)}
+        out["d"].zero_()
+        check(lib.trajopt_debug_linearize(self._h, _ptr(out["F_x"]), _ptr(out["F_u"]), _ptr(out["d"]), _ptr(out["L"]),
+                                          _ptr(out["L_x"]), _ptr(out["L_xx"]), _ptr(out["L_u"]), _stream(self.device)))
+        return out
+
+    def debug_gains(self):
+        k = self._new(self.B, self.N, self.NU)
+        K = self._new(self.B, self.N, self.NU, self.NX)
+        check(lib.trajopt_debug_gains(self._h, _ptr(k), _ptr(K), _stream(self.device)))
+        return k, K
+
+    def set_profiling(self, on):
+        check(lib.trajopt_set_profiling(self._h, int(bool(on))))
+
+    def phase_times(self, reset=True):
+        ms = (C.c_double * 4)()
+        cnt = (C.c_int64 * 4)()
+        check(lib.trajopt_phase_times(self._h, ms, cnt, int(reset)))
+        names = ("linearize", "backward", "forward", "other")
+        return {n: (ms[i], cnt[i]) for i, n in enumerate(names)}
+
+
+def lie_op(name, x, device="cuda"):
+    """Evaluate one Lie-group primitive of the device library on rows of `x` (parity tests)."""
+    code, win, wout = _lib.LIE_OPS[name]
+    t = torch.as_tensor(np.asarray(x, dtype=np.float64)).reshape(-1, win).contiguous().to(device)
+    out = torch.empty(t.shape[0], wout, dtype=torch.float64, device=t.device)
+    check(lib.trajopt_debug_lie(code, t.shape[0], _ptr(t), _ptr(out), _stream(t.device)))
+    return out
+
+
+def launch_count(reset=False):
+    return int(lib.trajopt_launch_count(int(reset)))
