@@ -135,6 +135,11 @@ int trajopt_debug_gains(trajopt_handle* h, double* d_k, double* d_K, void* strea
 /* Lie-group primitives on n independent inputs (problem-major rows), see csrc/api.cu for op codes */
 int trajopt_debug_lie(int op, int n, const double* d_in, double* d_out, void* stream);
 
+/* measured FP64 FMA throughput of the current device (the roofline denominator of this path: there is
+ * no FP64 figure in MEASURED_PEAKS.json).  Runs a register-only DFMA kernel for about `ms_target`
+ * milliseconds, timed with CUDA events; *out_tflops = 2 * DFMA / time. */
+int trajopt_debug_fp64_peak(double ms_target, double* out_tflops, void* stream);
+
 /* kernels launched by this library since the last reset (for bench.py's gpu_launches claim) */
 int64_t trajopt_launch_count(int reset);
 /* device seconds spent in the phases of the last trajopt_iterate calls since reset:

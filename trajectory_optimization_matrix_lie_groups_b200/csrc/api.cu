@@ -687,6 +687,42 @@ int trajopt_debug_lie(int op, int n, const double* d_in, double* d_out, void* st
     return 0;
 }
 
+int trajopt_debug_fp64_peak(double ms_target, double* out_tflops, void* stream) {
+    if (!out_tflops) return fail(TRAJOPT_E_INVALID, "trajopt_debug_fp64_peak: NULL argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    int dev = 0, sms = 0;
+    CUDA_OK(cudaGetDevice(&dev));
+    CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int blocks = sms * 8, threads = 256;
+    double* sink = nullptr;
+    CUDA_OK(cudaMalloc((void**)&sink, (size_t)blocks * threads * sizeof(double)));
+    cudaEvent_t e0, e1;
+    CUDA_OK(cudaEventCreate(&e0));
+    CUDA_OK(cudaEventCreate(&e1));
+    int iters = 2000;
+    double best = 0.0;
+    for (int rep = 0; rep < 6; ++rep) {
+        CUDA_OK(cudaEventRecord(e0, s));
+        LAUNCH(k_fp64_peak, blocks, threads, 0, s, iters, 1.0, sink);
+        CUDA_OK(cudaEventRecord(e1, s));
+        CUDA_OK(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+        const double flop = 2.0 * 64.0 * (double)iters * (double)blocks * threads;
+        const double tf = flop / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+        if (rep == 0 && ms > 0.f && ms_target > 0.0) {   // rescale the loop length to the requested duration
+            const double scale = ms_target / ms;
+            iters = (int)fmin(2.0e6, fmax(500.0, iters * scale));
+        }
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    *out_tflops = best;
+    return 0;
+}
+
 int trajopt_phase_times(trajopt_handle* h, double* out_ms, int64_t* cnt, int reset) {
     if (!h) return fail(TRAJOPT_E_INVALID, "trajopt_phase_times: NULL handle");
     for (int i = 0; i < PH_COUNT; ++i) {

@@ -106,4 +106,19 @@ __global__ void k_debug_lie(int op, int n, const double* __restrict__ in, double
     for (int j = 0; j < lie_out_width(op); ++j) y[j] = o[j];
 }
 
+// FP64 FMA peak: 8 independent dependent-chains of DFMA per thread, enough warps to fill every SM.
+// 2 flop per DFMA; the result is stored so the chains cannot be removed.
+__global__ void __launch_bounds__(256) k_fp64_peak(int iters, double seed, double* __restrict__ sink) {
+    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 0.999999, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+            a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+        }
+    }
+    sink[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
 }  // namespace trajopt

@@ -244,3 +244,12 @@ def lie_op(name, x, device="cuda"):
 
 def launch_count(reset=False):
     return int(lib.trajopt_launch_count(int(reset)))
+
+
+def fp64_peak_tflops(ms_target=50.0, device=None):
+    """Measured FP64 FMA throughput of the current device (roofline denominator), TFLOP/s."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    out = C.c_double(0.0)
+    with torch.cuda.device(dev):
+        check(lib.trajopt_debug_fp64_peak(float(ms_target), C.byref(out), _stream(dev)))
+    return out.value
