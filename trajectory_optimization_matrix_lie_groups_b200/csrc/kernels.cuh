@@ -406,362 +406,4 @@ __device__ inline double pairwise_sum(const double* a, size_t stride, int n) {
     return ret;
 }
 
-// ------------------------------------------------------------------------------------------
-// Backward Riccati sweep.  grid = Bp/32 blocks of one warp; thread = problem.
-// Shared memory (per thread column, stride 32 doubles => conflict-free 64-bit accesses):
-//   Vs  packed upper triangle of V_xx(i+1)            NX(NX+1)/2
-//   Vn  V_xx(i) under construction                    NX(NX+1)/2
-//   Ys  Y = L^-1 Q_ux, first NX-3 columns             NU (NX-3)
-// Algebra per stage (equivalent to :3052-3060, :2993-3004 up to rounding):
-//   v = V_x + V_xx d;  Q_x = l_x + A^T v;  Q_u = l_u + B^T v;  X = V_xx A;
-//   Q_xx = l_xx + A^T X;  Q_ux = B^T (X + mu A);  Q_uu = l_uu + B^T (V_xx + mu I) B = L L^T
-//   Y = L^-1 Q_ux, y = L^-1 Q_u;  K = -L^-T Y, k = -L^-T y;
-//   V_x(i) = Q_x - Y^T y  (= Q_x + K^T Q_uu k + K^T Q_u + Q_ux^T k);
-//   V_xx(i) = Q_xx - Y^T Y (= sym(Q_xx + K^T Q_uu K + K^T Q_ux + Q_ux^T K)), symmetric by construction.
-// ------------------------------------------------------------------------------------------
-template <int KIND> constexpr int bwd_smem_doubles() {
-    using D = Dims<KIND>;
-    return D::NX * (D::NX + 1) + D::NU * (D::NX - 3);
-}
-
-template <int KIND, bool MS>
-__global__ void __launch_bounds__(kBlock) k_backward(const Params prm, Work w, int it) {
-    using D = Dims<KIND>;
-    using LR = LinRec<KIND>;
-    constexpr int NX = D::NX, NP = D::NP, NU = D::NU, NV = NX - NP, F = LR::LEN;
-    constexpr int NT = NX * (NX + 1) / 2;
-    constexpr int NYC = NX - 3;      // columns of Y kept in shared memory
-    extern __shared__ double sm[];
-    const int lane = threadIdx.x;
-    const int b = blockIdx.x * kBlock + lane;
-    if (b >= prm.B || w.status[b] != TRAJOPT_RUNNING) return;
-    const int Bp = prm.Bp, N = prm.N;
-    double* Vs = sm + lane;
-    double* Vn = sm + NT * kBlock + lane;
-    double* Ys = sm + 2 * NT * kBlock + lane;
-    const double* lin = w.lin;
-
-    // ---- cost / defect of the current trajectory ----------------------------------------
-    double Jcur, dn = 0.0;
-    if constexpr (MS) {
-        // J_new of the previous iteration: Python sum, left to right, + terminal (:2742-2754)
-        double s = 0.0;
-        for (int i = 0; i < N; ++i) s += w.Lc[(size_t)i * Bp + b];
-        Jcur = s + w.Lc[(size_t)N * Bp + b];
-        double q = 0.0;
-        for (int i = 0; i < N; ++i) q += w.Dsq[(size_t)i * Bp + b];
-        dn = sqrt(q);
-        w.dnorm[b] = dn;
-        if (it > 0) w.Jhist[(size_t)(it - 1) * Bp + b] = Jcur;
-        w.defhist[(size_t)it * Bp + b] = dn;
-    } else {
-        Jcur = pairwise_sum(w.Lc + b, (size_t)Bp, N + 1);      // J_opt = L.sum() (:1935)
-    }
-    w.J[b] = Jcur;
-    if (!isfinite(Jcur)) {
-        w.status[b] = TRAJOPT_NO_DESCENT | TRAJOPT_FLAG_NONFINITE;
-        return;
-    }
-    if (it >= prm.max_iters) {          // MS only: closing pass after the last rollout
-        w.status[b] = TRAJOPT_MAX_ITER | (w.status[b] & ~15);
-        return;
-    }
-
-    // ---- terminal condition: V_x = l_x(N), V_xx = l_xx(N) --------------------------------
-    double Vx[NX];
-#pragma unroll
-    for (int j = 0; j < NX; ++j) Vx[j] = lin[soa(N, LR::LX_OFF + j, F, Bp, b)];
-#pragma unroll
-    for (int r = 0; r < NX; ++r)
-#pragma unroll
-        for (int c = r; c < NX; ++c) {
-            double v;
-            if (c < NP) v = lin[soa(N, LR::LXX_OFF + tri_idx(NP, r, c), F, Bp, b)];
-            else if (r >= NP) v = 2.0 * prm.P2[(r - NP) * NV + (c - NP)];
-            else v = 0.0;
-            Vs[tri_idx(NX, r, c) * kBlock] = v;
-        }
-    double pad[NX];                      // SS: adjoint variable p (:2339)
-#pragma unroll
-    for (int j = 0; j < NX; ++j) pad[j] = Vx[j];
-
-    double mu = w.mu[b], delta = w.delta[b];
-    double gsum = 0.0;
-    int flags = 0;
-
-    // B^T B (constant)
-    double BtB[NU * NU];
-#pragma unroll
-    for (int a = 0; a < NU; ++a)
-#pragma unroll
-        for (int c = a; c < NU; ++c) {
-            double s = 0.0;
-#pragma unroll
-            for (int r = 0; r < NV; ++r)
-                if (bv_nz<KIND>(r, a) && bv_nz<KIND>(r, c)) s += prm.Bv[r * NU + a] * prm.Bv[r * NU + c];
-            BtB[a * NU + c] = s;
-        }
-
-    for (int i = N - 1; i >= 0; --i) {
-        AMat<KIND> A;
-        A.load(lin, i, Bp, b);
-
-        // (1) v = V_x + V_xx d
-        double v[NX];
-        if constexpr (MS) {
-            double d[NX];
-#pragma unroll
-            for (int j = 0; j < NX; ++j) d[j] = lin[soa(i, LR::D_OFF + j, F, Bp, b)];
-#pragma unroll
-            for (int r = 0; r < NX; ++r) {
-                double s = Vx[r];
-#pragma unroll
-                for (int c = 0; c < NX; ++c) s += Vs[sym_idx(NX, r, c) * kBlock] * d[c];
-                v[r] = s;
-            }
-        } else {
-#pragma unroll
-            for (int r = 0; r < NX; ++r) v[r] = Vx[r];
-        }
-
-        // (2) Q_x = l_x + A^T v ;  Q_u = l_u + Bv^T v_vel
-        double Qx[NX], Qu[NU], lu[NU];
-#pragma unroll
-        for (int c = 0; c < NX; ++c) {
-            double s = lin[soa(i, LR::LX_OFF + c, F, Bp, b)];
-#pragma unroll
-            for (int r = 0; r < NX; ++r)
-                if (AMat<KIND>::nz(r, c)) s += A.get(r, c) * v[r];
-            Qx[c] = s;
-        }
-#pragma unroll
-        for (int a = 0; a < NU; ++a) lu[a] = lin[soa(i, LR::LU_OFF + a, F, Bp, b)];
-#pragma unroll
-        for (int a = 0; a < NU; ++a) {
-            double s = lu[a];
-#pragma unroll
-            for (int r = 0; r < NV; ++r)
-                if (bv_nz<KIND>(r, a)) s += prm.Bv[r * NU + a] * v[NP + r];
-            Qu[a] = s;
-        }
-        if constexpr (MS) {
-            // g_t = L_u + F_u^T (V_x + V_xx^T d) = Q_u (:3090)
-            double q = 0.0;
-#pragma unroll
-            for (int a = 0; a < NU; ++a) q += Qu[a] * Qu[a];
-            gsum += sqrt(q);
-        } else {
-            // adjoint recursion of the SS gradient (:2343-2346): g = l_u + B^T p ; p = l_x + A^T p
-            double g2 = 0.0;
-#pragma unroll
-            for (int a = 0; a < NU; ++a) {
-                double s = lu[a];
-#pragma unroll
-                for (int r = 0; r < NV; ++r)
-                    if (bv_nz<KIND>(r, a)) s += prm.Bv[r * NU + a] * pad[NP + r];
-                g2 += s * s;
-            }
-            gsum += sqrt(g2);
-            double pn[NX];
-#pragma unroll
-            for (int c = 0; c < NX; ++c) {
-                double s = lin[soa(i, LR::LX_OFF + c, F, Bp, b)];
-#pragma unroll
-                for (int r = 0; r < NX; ++r)
-                    if (AMat<KIND>::nz(r, c)) s += A.get(r, c) * pad[r];
-                pn[c] = s;
-            }
-#pragma unroll
-            for (int c = 0; c < NX; ++c) pad[c] = pn[c];
-        }
-
-        // (3) Q_uu0 = l_uu + Bv^T V_vv Bv  (upper triangle)
-        double Quu0[NU * NU];
-        {
-            double T[NV * NU];           // V_vv Bv
-#pragma unroll
-            for (int r = 0; r < NV; ++r)
-#pragma unroll
-                for (int a = 0; a < NU; ++a) {
-                    double s = 0.0;
-#pragma unroll
-                    for (int k = 0; k < NV; ++k)
-                        if (bv_nz<KIND>(k, a)) s += Vs[sym_idx(NX, NP + r, NP + k) * kBlock] * prm.Bv[k * NU + a];
-                    T[r * NU + a] = s;
-                }
-#pragma unroll
-            for (int a = 0; a < NU; ++a)
-#pragma unroll
-                for (int c = a; c < NU; ++c) {
-                    double s = 2.0 * prm.R[a * NU + c];
-                    if (a == c) s += lin[soa(i, LR::LUU_OFF + a, F, Bp, b)];
-#pragma unroll
-                    for (int r = 0; r < NV; ++r)
-                        if (bv_nz<KIND>(r, a)) s += prm.Bv[r * NU + a] * T[r * NU + c];
-                    Quu0[a * NU + c] = s;
-                }
-        }
-
-        // (4) regularisation loop (:2221-2246 / :2964-2991): Cholesky of Q_uu0 + mu B^T B
-        double Lc[NU * NU];              // lower factor, Lc[r][c] for c < r; diagonal stores 1/L_rr
-        double mu_used;                  // the mu this stage's Q_ux / Q_uu are formed with (:2311-2313)
-        bool gave_up = false;
-        while (true) {
-            mu_used = mu;
-            bool pd = true;
-#pragma unroll
-            for (int c = 0; c < NU; ++c) {
-                double dg = Quu0[c * NU + c] + mu_used * BtB[c * NU + c];
-#pragma unroll
-                for (int k = 0; k < c; ++k) dg -= Lc[c * NU + k] * Lc[c * NU + k];
-                if (!(dg > 0.0)) pd = false;
-                const double inv = rsqrt(dg);
-                Lc[c * NU + c] = inv;
-#pragma unroll
-                for (int r = c + 1; r < NU; ++r) {
-                    double s = Quu0[c * NU + r] + mu_used * BtB[c * NU + r];
-#pragma unroll
-                    for (int k = 0; k < c; ++k) s -= Lc[r * NU + k] * Lc[c * NU + k];
-                    Lc[r * NU + c] = s * inv;
-                }
-            }
-            if (!pd) {
-                delta = fmax(1.0, delta) * prm.delta0;
-                mu = fmax(prm.mu_min, mu * delta);
-                if (prm.mu_max > 0.0 && mu >= prm.mu_max) { gave_up = true; break; }
-            } else {
-                delta = fmin(1.0, delta) / prm.delta0;
-                mu *= delta;
-                if (mu <= prm.mu_min) mu = 0.0;
-                break;
-            }
-        }
-        if (gave_up) {
-            // The reference warns and carries on with a non-PD Q_uu (:2238-2240); such a problem
-            // has already diverged.  It is stopped here and flagged.
-            flags |= TRAJOPT_FLAG_REG_EXCEEDED;
-            break;
-        }
-
-        // y = L^-1 Q_u
-        double y[NU];
-#pragma unroll
-        for (int r = 0; r < NU; ++r) {
-            double s = Qu[r];
-#pragma unroll
-            for (int k = 0; k < r; ++k) s -= Lc[r * NU + k] * y[k];
-            y[r] = s * Lc[r * NU + r];
-        }
-        // k = -L^-T y
-        {
-            double kk[NU];
-#pragma unroll
-            for (int r = NU - 1; r >= 0; --r) {
-                double s = y[r];
-#pragma unroll
-                for (int k = r + 1; k < NU; ++k) s -= Lc[k * NU + r] * kk[k];
-                kk[r] = s * Lc[r * NU + r];
-            }
-#pragma unroll
-            for (int a = 0; a < NU; ++a) w.kff[soa(i, a, NU, Bp, b)] = -kk[a];
-        }
-
-        // (5) column blocks of 3
-        double Vxn[NX];
-#pragma unroll
-        for (int cb = 0; cb < NX / 3; ++cb) {
-            double X[NX][3];
-#pragma unroll
-            for (int r = 0; r < NX; ++r)
-#pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                    double s = 0.0;
-#pragma unroll
-                    for (int k = 0; k < NX; ++k)
-                        if (AMat<KIND>::nz(k, cb * 3 + j)) s += Vs[sym_idx(NX, r, k) * kBlock] * A.get(k, cb * 3 + j);
-                    X[r][j] = s;
-                }
-            double Y[NU][3];
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                const int c = cb * 3 + j;
-                // Q_ux[:, c] = Bv^T (X_vel[:, c] + mu A_vel[:, c])
-                double q[NU];
-#pragma unroll
-                for (int a = 0; a < NU; ++a) {
-                    double s = 0.0;
-#pragma unroll
-                    for (int r = 0; r < NV; ++r)
-                        if (bv_nz<KIND>(r, a)) {
-                            double t = X[NP + r][j];
-                            if (AMat<KIND>::nz(NP + r, c)) t += mu_used * A.get(NP + r, c);
-                            s += prm.Bv[r * NU + a] * t;
-                        }
-                    q[a] = s;
-                }
-#pragma unroll
-                for (int r = 0; r < NU; ++r) {
-                    double s = q[r];
-#pragma unroll
-                    for (int k = 0; k < r; ++k) s -= Lc[r * NU + k] * Y[k][j];
-                    Y[r][j] = s * Lc[r * NU + r];
-                }
-                double kk[NU];
-#pragma unroll
-                for (int r = NU - 1; r >= 0; --r) {
-                    double s = Y[r][j];
-#pragma unroll
-                    for (int k = r + 1; k < NU; ++k) s -= Lc[k * NU + r] * kk[k];
-                    kk[r] = s * Lc[r * NU + r];
-                }
-#pragma unroll
-                for (int a = 0; a < NU; ++a) w.Kfb[soa(i, a * NX + c, NU * NX, Bp, b)] = -kk[a];
-                if (c < NYC) {
-#pragma unroll
-                    for (int a = 0; a < NU; ++a) Ys[(a * NYC + c) * kBlock] = Y[a][j];
-                }
-                // V_x(i)[c] = Q_x[c] - Y[:,c]^T y
-                double s = Qx[c];
-#pragma unroll
-                for (int a = 0; a < NU; ++a) s -= Y[a][j] * y[a];
-                Vxn[c] = s;
-            }
-            // V_xx(i)[r][c], r <= c
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                const int c = cb * 3 + j;
-#pragma unroll
-                for (int r = 0; r <= c; ++r) {
-                    double s;
-                    if (c < NP) s = lin[soa(i, LR::LXX_OFF + tri_idx(NP, r, c), F, Bp, b)];
-                    else if (r >= NP) s = 2.0 * prm.W2[(r - NP) * NV + (c - NP)];
-                    else s = 0.0;
-#pragma unroll
-                    for (int k = 0; k < NX; ++k)
-                        if (AMat<KIND>::nz(k, r)) s += A.get(k, r) * X[k][j];
-#pragma unroll
-                    for (int a = 0; a < NU; ++a) {
-                        const double yr = (r >= cb * 3) ? Y[a][r - cb * 3] : Ys[(a * NYC + r) * kBlock];
-                        s -= yr * Y[a][j];
-                    }
-                    Vn[tri_idx(NX, r, c) * kBlock] = s;
-                }
-            }
-        }
-#pragma unroll
-        for (int c = 0; c < NX; ++c) Vx[c] = Vxn[c];
-        { double* t = Vs; Vs = Vn; Vn = t; }
-    }
-
-    w.mu[b] = mu;
-    w.delta[b] = delta;
-    const double g = gsum / (double)N;
-    w.grad[b] = g;
-    w.gradhist[(size_t)it * Bp + b] = g;
-    int st = TRAJOPT_RUNNING;
-    if (flags & TRAJOPT_FLAG_REG_EXCEEDED) st = TRAJOPT_NO_DESCENT;
-    else if (MS ? (g < prm.tol_grad && dn < prm.tol_defect) : (g < prm.tol_grad)) st = TRAJOPT_CONVERGED;
-    w.status[b] = st | flags;
-}
-
 }  // namespace trajopt

@@ -1,6 +1,7 @@
 // Forward passes, line-search bookkeeping, augmented-Lagrangian update and layout exports.
 #pragma once
 #include "kernels.cuh"
+#include "backward.cuh"
 
 namespace trajopt {
 
