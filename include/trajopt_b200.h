@@ -132,6 +132,14 @@ int trajopt_debug_linearize(trajopt_handle* h, double* d_Fx, double* d_Fu, doubl
                             double* d_Lx, double* d_Lxx, double* d_Lu, void* stream);
 /* gains of the last backward pass: d_k [B][N][NU], d_K [B][N][NU][NX] */
 int trajopt_debug_gains(trajopt_handle* h, double* d_k, double* d_K, void* stream);
+/* the reference's per-stage callbacks on n independent rows against reference row i (0 <= i <= N):
+ * d_x [n][NS], d_u [n][NU] (ignored when terminal); outputs, any may be NULL: d_f [n][NS] = f(x,u),
+ * d_Fx [n][NX][NX], d_Fu [n][NX][NU], d_l [n], d_lx [n][NX], d_lxx [n][NX][NX], d_lu [n][NU],
+ * d_err [n][NX] = [Log(q q_ref_i^-1); xi - xi_ref_i]   (BaseDynamics.f/f_x/f_u traopt_dynamics.py:24-64,
+ * BaseCost.l/l_x/l_u/l_xx traopt_cost.py:14-110, cost._err :659-673) */
+int trajopt_debug_stage(trajopt_handle* h, int i, int terminal, int n, const double* d_x, const double* d_u,
+                        double* d_f, double* d_Fx, double* d_Fu, double* d_l, double* d_lx, double* d_lxx,
+                        double* d_lu, double* d_err, void* stream);
 /* Lie-group primitives on n independent inputs (problem-major rows), see csrc/api.cu for op codes */
 int trajopt_debug_lie(int op, int n, const double* d_in, double* d_out, void* stream);
 

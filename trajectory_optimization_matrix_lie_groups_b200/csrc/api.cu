@@ -320,6 +320,14 @@ int debug_linearize_impl(trajopt_handle* h, double* Fx, double* Fu, double* dd, 
     return 0;
 }
 
+template <int KIND>
+int debug_stage_impl(trajopt_handle* h, int i, int terminal, int n, const double* x, const double* u, double* f,
+                     double* Fx, double* Fu, double* l, double* lx, double* lxx, double* lu, double* err, cudaStream_t s) {
+    LAUNCH((k_debug_stage<KIND>), blocks_for(n, 64), 64, 0, s, h->prm, h->d_ref, i, terminal, n, x, u, f, Fx, Fu, l, lx,
+           lxx, lu, err);
+    return 0;
+}
+
 #define DISPATCH_KIND(h, fn, ...)                                             \
     ((h)->kind == TRAJOPT_SO3   ? fn<TRAJOPT_SO3>(__VA_ARGS__)                \
      : (h)->kind == TRAJOPT_SE3 ? fn<TRAJOPT_SE3>(__VA_ARGS__)                \
@@ -677,6 +685,19 @@ int trajopt_debug_gains(trajopt_handle* h, double* d_k, double* d_K, void* strea
     if (d_k) LAUNCH(k_export_traj, dim3(bg, h->N), 128, 0, s, h->B, h->Bp, h->NU, h->w.kff, h->w.kff, (const int*)nullptr, d_k, h->N);
     if (d_K) LAUNCH(k_export_traj, dim3(bg, h->N), 128, 0, s, h->B, h->Bp, h->NU * h->NX, h->w.Kfb, h->w.Kfb, (const int*)nullptr, d_K, h->N);
     return 0;
+}
+
+int trajopt_debug_stage(trajopt_handle* h, int i, int terminal, int n, const double* d_x, const double* d_u, double* d_f,
+                        double* d_Fx, double* d_Fu, double* d_l, double* d_lx, double* d_lxx, double* d_lu, double* d_err,
+                        void* stream) {
+    if (!h || !d_x) return fail(TRAJOPT_E_INVALID, "trajopt_debug_stage: NULL argument");
+    if (!h->have_params || !h->have_ref) return fail(TRAJOPT_E_STATE, "trajopt_debug_stage: set_params and set_reference first");
+    if (i < 0 || i > h->N || n < 0) return fail(TRAJOPT_E_INVALID, "trajopt_debug_stage: stage index out of range");
+    if (!terminal && !d_u) return fail(TRAJOPT_E_INVALID, "trajopt_debug_stage: d_u is NULL for a non-terminal stage");
+    if (n == 0) return 0;
+    DeviceGuard guard(h->device);
+    return DISPATCH_KIND(h, debug_stage_impl, h, i, terminal, n, d_x, d_u, d_f, d_Fx, d_Fu, d_l, d_lx, d_lxx, d_lu, d_err,
+                         (cudaStream_t)stream);
 }
 
 int trajopt_debug_lie(int op, int n, const double* d_in, double* d_out, void* stream) {

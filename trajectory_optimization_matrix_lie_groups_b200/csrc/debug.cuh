@@ -1,7 +1,7 @@
 // Lie-group primitives exposed one by one for the parity tests (trajopt_debug_lie).
 // Rows are problem-major: input row r at d_in + r * in_width(op), output at d_out + r * out_width(op).
 #pragma once
-#include "lie.cuh"
+#include "backward.cuh"
 
 namespace trajopt {
 
@@ -104,6 +104,107 @@ __global__ void k_debug_lie(int op, int n, const double* __restrict__ in, double
         default: break;
     }
     for (int j = 0; j < lie_out_width(op); ++j) y[j] = o[j];
+}
+
+// Per-stage callbacks of the reference's Dynamics / Cost classes on n independent (x, u) rows against
+// reference row i: f (traopt_dynamics.py:763-787, 369-380, 1373-1401), f_x / f_u (:802-850, 385-403,
+// 1416-1482), l / l_x / l_xx / l_u (traopt_cost.py:675-867, 381-564) and the tracking error _err.
+template <int KIND>
+__global__ void k_debug_stage(const Params prm, const double* __restrict__ ref, int i, int terminal, int n,
+                              const double* __restrict__ xin, const double* __restrict__ uin, double* f_out,
+                              double* Fx, double* Fu, double* l_out, double* lx_out, double* lxx_out, double* lu_out,
+                              double* err_out) {
+    using D = Dims<KIND>;
+    using LR = LinRec<KIND>;
+    constexpr int NX = D::NX, NP = D::NP, NU = D::NU, NS = D::NS, NV = NX - NP, NB = NX / 3;
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const double* refrow = ref + (size_t)i * RefRow<KIND>::N;
+    State<KIND> x;
+    {
+        double row[NS];
+        for (int j = 0; j < NS; ++j) row[j] = xin[(size_t)r * NS + j];
+        quat_normalize(row);
+        for (int j = 0; j < 4; ++j) x.q[j] = row[j];
+        if constexpr (KIND != TRAJOPT_SO3) {
+            for (int j = 0; j < 3; ++j) x.p[j] = row[4 + j];
+            for (int j = 0; j < 6; ++j) x.xi[j] = row[7 + j];
+        } else {
+            for (int j = 0; j < 3; ++j) x.xi[j] = row[4 + j];
+        }
+    }
+    double u[NU];
+    for (int j = 0; j < NU; ++j) u[j] = (uin && !terminal) ? uin[(size_t)r * NU + j] : 0.0;
+    if (f_out) {
+        State<KIND> xn;
+        dyn_step<KIND>(prm, x, u, xn);
+        double* o = f_out + (size_t)r * NS;
+        for (int j = 0; j < 4; ++j) o[j] = xn.q[j];
+        if constexpr (KIND != TRAJOPT_SO3) {
+            for (int j = 0; j < 3; ++j) o[4 + j] = xn.p[j];
+            for (int j = 0; j < 6; ++j) o[7 + j] = xn.xi[j];
+        } else {
+            for (int j = 0; j < 3; ++j) o[4 + j] = xn.xi[j];
+        }
+    }
+    if (Fx) {
+        double rec[LR::A_LEN];
+        dyn_jacobian<KIND>(prm, x, rec);
+        double* o = Fx + (size_t)r * NX * NX;
+        for (int j = 0; j < NX * NX; ++j) o[j] = 0.0;
+        sfor<0, NB>([&](auto rbc) {
+            sfor<0, NB>([&](auto cbc) {
+                constexpr int RB = decltype(rbc)::value, CB = decltype(cbc)::value;
+                if constexpr (blk_kind<KIND>(RB, CB) != BK_ZERO) {
+                    double m[9];
+                    load_blk<KIND, RB, CB>(rec, 1, m);
+                    for (int a = 0; a < 3; ++a)
+                        for (int c = 0; c < 3; ++c) o[(RB * 3 + a) * NX + CB * 3 + c] = m[3 * a + c];
+                }
+            });
+        });
+    }
+    if (Fu) {
+        double* o = Fu + (size_t)r * NX * NU;
+        for (int a = 0; a < NX; ++a)
+            for (int c = 0; c < NU; ++c) o[a * NU + c] = (a >= NP && bv_nz<KIND>(a - NP, c)) ? prm.Bv[(a - NP) * NU + c] : 0.0;
+    }
+    if (l_out || lx_out || lxx_out) {
+        double lx[NX], lxx[LR::LXX_LEN];
+        double val = cost_expand<KIND>(prm, x, refrow, terminal != 0, lx, lxx);
+        if (!terminal) {
+            for (int a = 0; a < NU; ++a) {
+                double sacc = 0.0;
+                for (int c = 0; c < NU; ++c) sacc += prm.R[a * NU + c] * u[c];
+                val += u[a] * sacc;
+            }
+        }
+        if (l_out) l_out[r] = val;
+        if (lx_out) for (int j = 0; j < NX; ++j) lx_out[(size_t)r * NX + j] = lx[j];
+        if (lxx_out) {
+            const double* W2 = terminal ? prm.P2 : prm.W2;
+            for (int a = 0; a < NX; ++a)
+                for (int c = 0; c < NX; ++c) {
+                    double v = 0.0;
+                    if (a < NP && c < NP) v = lxx[sym_idx(NP, a, c)];
+                    else if (a >= NP && c >= NP) v = 2.0 * W2[(a - NP) * NV + (c - NP)];
+                    lxx_out[((size_t)r * NX + a) * NX + c] = v;
+                }
+        }
+    }
+    if (lu_out) {
+        for (int a = 0; a < NU; ++a) {
+            double sacc = 0.0;
+            for (int c = 0; c < NU; ++c) sacc += prm.R[a * NU + c] * u[c];
+            lu_out[(size_t)r * NU + a] = terminal ? 0.0 : 2.0 * sacc;
+        }
+    }
+    if (err_out) {
+        double e[NP], dxi[NV];
+        tracking_error<KIND>(x, refrow, e, dxi);
+        for (int j = 0; j < NP; ++j) err_out[(size_t)r * NX + j] = e[j];
+        for (int j = 0; j < NV; ++j) err_out[(size_t)r * NX + NP + j] = dxi[j];
+    }
 }
 
 // FP64 FMA peak: 8 independent dependent-chains of DFMA per thread, enough warps to fill every SM.

@@ -222,6 +222,24 @@ class BatchSolver:
         check(lib.trajopt_debug_gains(self._h, _ptr(k), _ptr(K), _stream(self.device)))
         return k, K
 
+    def stage_eval(self, i, x_rows, u_rows=None, terminal=False, want=("f", "F_x", "F_u", "l", "l_x", "l_xx", "l_u", "err")):
+        """The reference's per-stage callbacks on rows of states/controls against reference row i."""
+        x = torch.as_tensor(np.asarray(x_rows, dtype=np.float64)).reshape(-1, self.NS).contiguous().to(self.device)
+        n = x.shape[0]
+        u = None
+        if not terminal:
+            u = torch.as_tensor(np.asarray(u_rows, dtype=np.float64)).reshape(-1, self.NU).contiguous().to(self.device)
+            if u.shape[0] != n:
+                raise ValueError("x and u row counts differ")
+        NX, NU, NS = self.NX, self.NU, self.NS
+        shapes = {"f": (n, NS), "F_x": (n, NX, NX), "F_u": (n, NX, NU), "l": (n,), "l_x": (n, NX), "l_xx": (n, NX, NX),
+                  "l_u": (n, NU), "err": (n, NX)}
+        out = {k: (self._new(*shapes[k]) if k in want else None) for k in shapes}
+        check(lib.trajopt_debug_stage(self._h, int(i), int(bool(terminal)), n, _ptr(x), _ptr(u), _ptr(out["f"]),
+                                      _ptr(out["F_x"]), _ptr(out["F_u"]), _ptr(out["l"]), _ptr(out["l_x"]),
+                                      _ptr(out["l_xx"]), _ptr(out["l_u"]), _ptr(out["err"]), _stream(self.device)))
+        return {k: v for k, v in out.items() if v is not None}
+
     def set_profiling(self, on):
         check(lib.trajopt_set_profiling(self._h, int(bool(on))))
 
