@@ -78,7 +78,7 @@ def cpu_sample(config, n_iters, iters_per_solve, cores=None):
 
     Returns (solves_per_second extrapolated to whole solves, cores, description)."""
     import multiprocessing as mp
-    cores = cores or len(os.sched_getaffinity(0))
+    cores = cores or int(os.environ.get("TRAJOPT_BENCH_CORES", "0")) or len(os.sched_getaffinity(0))
     batch = max(cores, 12)
     jobs = [(config, b, n_iters, batch) for b in range(cores)]
     t0 = time.perf_counter()

@@ -119,3 +119,31 @@ def test_se3_ms_n955_full(name, iters):
 def test_more_goldens(name, mode, n):
     g, kind, r = _run(name, mode, max_iter=n)
     _check_hist(r, g, mode, n=n, rtol=1e-11)
+
+
+def test_drone_ss_n500_line_search_walks_down_the_step_sizes():
+    """1st-draft quadrotor result file, single shooting: the reference's line search accepts step
+    indices 2,0,0,3,5,7,8,9,9,9,10,10,11,11 and then fails — decision parity at every rung."""
+    g, kind, r = _run("draft1_drone_n500", "ss")
+    assert r.iterations == 15 and r.status == solvers.STATUS_NO_DESCENT
+    assert r.alpha_hist == [2, 0, 0, 3, 5, 7, 8, 9, 9, 9, 10, 10, 11, 11, -1]
+    _check_hist(r, g, "ss")
+    _check_final(r, g, kind, "ss", 1e-8, 1e-10)
+
+
+def test_so3_draft1_both_methods():
+    for mode in ("ms", "ss"):
+        g, kind, r = _run("draft1_so3_n249", mode, max_iter=50)
+        assert r.iterations == 50
+        _check_hist(r, g, mode)
+        _check_final(r, g, kind, mode, 1e-10, 1e-12)
+
+
+@pytest.mark.slow
+def test_se3_ss_n955_line_search_decisions():
+    g, kind, r = _run("se3_n955_r1e-4", "ss")
+    assert r.iterations == 34 and r.alpha_hist == [0] * 32 + [1, -1]
+    _check_hist(r, g, "ss")
+    g, kind, r = _run("se3_n955_r1e-5", "ss", max_iter=32)
+    assert r.alpha_hist == [0] * 28 + [2, 8, 1, 11]
+    _check_hist(r, g, "ss")

@@ -179,7 +179,10 @@ __global__ void k_reset(const Params prm, Work w) {
     w.mu[b] = 1.0;
     w.delta[b] = prm.delta0;
     w.iters[b] = 0;
-    w.status[b] = (b < prm.B) ? TRAJOPT_RUNNING : TRAJOPT_MAX_ITER;
+    // n_iterations = 0: single shooting returns the initial rollout untouched; multiple shooting
+    // still runs its closing pass (cost / defect of the initial guess)
+    const bool run = (b < prm.B) && (prm.max_iters > 0 || prm.method != TRAJOPT_SS);
+    w.status[b] = run ? TRAJOPT_RUNNING : TRAJOPT_MAX_ITER;
     w.ls_state[b] = -2;
     w.J[b] = 0.0;
     w.grad[b] = 0.0;

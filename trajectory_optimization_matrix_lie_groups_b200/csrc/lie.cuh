@@ -4,7 +4,7 @@
 // scipy Rotation at every stage (traoptlibrary/traopt_utilis.py:331-399 and the manif
 // rplus / rminus / lminus / exp / log calls cited per function below).
 //
-// Conventions (same as SURVEY.md Appendix A and oracle/lie.py):
+// Conventions:
 //   * tangent = [omega, v] (angular first);
 //   * right perturbations: X (+) tau = X Exp(tau), A (-) B = Log(B^-1 A);
 //   * pose = unit quaternion [x, y, z, w] + translation; every compose renormalises the
