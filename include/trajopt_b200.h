@@ -132,6 +132,13 @@ int trajopt_debug_linearize(trajopt_handle* h, double* d_Fx, double* d_Fu, doubl
                             double* d_Lx, double* d_Lxx, double* d_Lu, void* stream);
 /* gains of the last backward pass: d_k [B][N][NU], d_K [B][N][NU][NX] */
 int trajopt_debug_gains(trajopt_handle* h, double* d_k, double* d_K, void* stream);
+/* line-search table of the last iteration, d_table [rows][B] (row-major, rows = trajopt_debug_linesearch_rows):
+ * single shooting: row a = J_new of step size a (traopt_controller.py:1972-1990);
+ * multiple shooting with line_search: rows [0, n_alphas) = J_new, [n_alphas, 2 n_alphas) = ||d_new|| of step size a
+ * (:2560-2576), then c1, c2 (expected cost change :2756-2769), defect weight (:2774-2788) and merit (:2556).
+ * Rows of step sizes that were not evaluated for a problem keep their previous content. */
+int trajopt_debug_linesearch_rows(trajopt_handle* h);
+int trajopt_debug_linesearch(trajopt_handle* h, double* d_table, void* stream);
 /* the reference's per-stage callbacks on n independent rows against reference row i (0 <= i <= N):
  * d_x [n][NS], d_u [n][NU] (ignored when terminal); outputs, any may be NULL: d_f [n][NS] = f(x,u),
  * d_Fx [n][NX][NX], d_Fu [n][NX][NU], d_l [n], d_lx [n][NX], d_lxx [n][NX][NX], d_lu [n][NU],

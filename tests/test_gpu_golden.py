@@ -3,7 +3,11 @@
 
 The bar of BASELINE.json's north star, asserted per golden:
   * the same iteration count and the same stopping reason;
-  * the same accepted step-size index at every iteration (single shooting line search);
+  * the same accepted step-size index at every iteration (single shooting line search) for as long
+    as the reference's own cost decrease is above rounding noise (relative decrease >= 1e-12; below
+    that `J_new < J_opt` compares two sums that differ in the last bits and the reference's own
+    decisions depend on manif's rounding — e.g. the N=955 SS result file ends with six iterations
+    whose J_hist *increases* by 1e-15 relative);
   * every cost-history entry within 1e-9 relative (observed <= 4e-12);
   * final controls / states within 1e-7 (observed <= 5e-10).
 """
@@ -64,7 +68,11 @@ def test_solve_matches_reference_results(name, method, n_iter, status, alphas):
     rel = np.abs(hist["J_hist"][0, :it] - Jg) / np.abs(Jg)
     assert rel.max() < J_RTOL
     if alphas is not None:
-        assert hist["alpha_hist"][0, :it].tolist() == alphas
+        dec = np.abs(np.diff(Jg)) / np.abs(Jg[1:])
+        noise = np.nonzero(dec < 1e-12)[0]
+        n_dec = int(noise[0]) + 1 if noise.size else it       # iterations whose decision is above rounding noise
+        n_dec = max(n_dec, min(it, 3))
+        assert hist["alpha_hist"][0, :n_dec].tolist() == alphas[:n_dec]
     elif method == "ms":
         assert np.all(hist["alpha_hist"][0, :it] == 0)
     if max_iters == n_gold or n_iter is None:
@@ -84,12 +92,11 @@ def test_solve_matches_reference_results(name, method, n_iter, status, alphas):
         assert np.max(np.abs(dh - dg[:n])) < 1e-9 * max(1.0, dg[0])
         gg = g["ms_grad_hist"]
         gh = hist["grad_hist"][0, :min(len(gg), it + 1)]
-        big = gg[:len(gh)] > 1e-9
-        assert np.max(np.abs(gh[big] - gg[:len(gh)][big]) / gg[:len(gh)][big]) < 1e-6
+        assert np.max(np.abs(gh - gg[:len(gh)]) / (gg[:len(gh)] + 1e-7)) < 1e-6      # 1e-6 relative down to 1e-7, absolute below
     else:
         gg = g["ss_grad_hist"]
         gh = hist["grad_hist"][0, :len(gg)]
-        assert np.max(np.abs(gh - gg) / gg) < 1e-6
+        assert np.max(np.abs(gh - gg) / (gg + 1e-7)) < 1e-6
 
 
 def test_headline_config_nominal_problem():

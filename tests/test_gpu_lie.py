@@ -1,10 +1,13 @@
 """GPU parity, level 1: the Lie-group closed forms of csrc/lie.cuh against the oracle (oracle/lie.py),
 called through the C ABI (`trajopt_debug_lie`).
 
-Tolerances (absolute, FP64): 1e-12 for everything except the SE(3) Jacobian block Q(omega, v) and
-what contains it (Jr, Jr^-1): manif's closed form `(1 - th^2/2 - cos th)/th^4` cancels
-catastrophically around th ~ 1e-3 (relative noise ~1e-16/th^4), so two correct FP64 evaluations
-that round differently agree only to ~1e-10 there; 1e-9 is asserted.
+Tolerances (absolute, FP64).  manif (and therefore the oracle) switches from the closed forms to a
+two-term series only below theta^2 = 1e-10; just above that threshold its closed forms cancel:
+`(1 - cos th)/th^2` carries a relative error of ~1e-16/th^2 and `(1 - th^2/2 - cos th)/th^4` one of
+~1e-16/th^4.  The device keeps longer series up to a larger angle (it is the more accurate of the
+two there), so the two agree to ~1e-11 on the SO(3) Jacobians / SE(3) exp-log and to ~1e-10 on the
+SE(3) Jacobian block Q(omega, v) (and on Jr, Jr^-1 which contain it) — far below the 1e-9 / 1e-7
+bars of the solver-level parity tests, which are the contract.  Asserted here: 1e-10 and 1e-9.
 """
 import numpy as np
 import pytest
@@ -31,10 +34,10 @@ def _op(name, x):
 
 @pytest.mark.parametrize("name,fn,tol", [
     ("so3_exp", lie.so3_exp, 1e-14),
-    ("so3_jr", lambda a: lie.so3_jr(a).ravel(), 1e-12),
-    ("so3_jr_inv", lambda a: lie.so3_jr_inv(a).ravel(), 1e-12),
-    ("so3_jl", lambda a: lie.so3_jl(a).ravel(), 1e-12),
-    ("so3_jl_inv", lambda a: lie.so3_jl_inv(a).ravel(), 1e-12),
+    ("so3_jr", lambda a: lie.so3_jr(a).ravel(), 1e-10),
+    ("so3_jr_inv", lambda a: lie.so3_jr_inv(a).ravel(), 1e-10),
+    ("so3_jl", lambda a: lie.so3_jl(a).ravel(), 1e-10),
+    ("so3_jl_inv", lambda a: lie.so3_jl_inv(a).ravel(), 1e-10),
 ])
 def test_so3_maps(name, fn, tol):
     w = _angles()
@@ -47,6 +50,7 @@ def test_so3_maps(name, fn, tol):
 
 def test_so3_log_roundtrip_and_oracle():
     w = _angles()
+    w = w[np.linalg.norm(w, axis=1) < np.pi]       # Log(Exp(w)) = w only inside the injectivity radius
     q = np.stack([lie.so3_exp(r) for r in w])
     got = _op("so3_log", q)
     ref = np.stack([lie.so3_log(r) for r in q])
@@ -59,7 +63,7 @@ def test_so3_log_roundtrip_and_oracle():
 
 
 @pytest.mark.parametrize("name,fn,tol", [
-    ("se3_exp", lambda a: np.concatenate(lie.se3_exp(a)), 1e-12),
+    ("se3_exp", lambda a: np.concatenate(lie.se3_exp(a)), 1e-10),
     ("se3_Q", lambda a: lie.se3_Q(a[:3], a[3:]).ravel(), 1e-9),
     ("se3_jr", lambda a: lie.se3_jr(a).ravel(), 1e-9),
     ("se3_jr_inv", lambda a: lie.se3_jr_inv(a).ravel(), 1e-9),
@@ -83,7 +87,7 @@ def test_se3_group_operations():
     qp = np.stack([np.concatenate(lie.se3_exp(r)) for r in tau])
     got = _op("se3_log", qp)
     ref = np.stack([lie.se3_log(r[:4], r[4:]) for r in qp])
-    assert np.max(np.abs(got - ref)) < 1e-12
+    assert np.max(np.abs(got - ref)) < 1e-10
     got = _op("se3_adj", qp)
     ref = np.stack([lie.se3_adj(r[:4], r[4:]).ravel() for r in qp])
     assert np.max(np.abs(got - ref)) < 1e-13
@@ -99,7 +103,7 @@ def test_se3_group_operations():
         err = np.abs(got - ref)
         if name == "se3_compose":      # quaternion sign is free
             err = np.minimum(err, np.abs(np.concatenate((-got[:, :4], got[:, 4:]), axis=1) - ref))
-        assert np.max(err) < 1e-11, name
+        assert np.max(err) < 1e-10, name
 
 
 def test_empty_and_bad_arguments():

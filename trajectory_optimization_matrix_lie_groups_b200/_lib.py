@@ -76,6 +76,8 @@ SYMBOLS = {
     "trajopt_solve_host": (_I, [_P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
     "trajopt_debug_linearize": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "trajopt_debug_gains": (_I, [_P, _P, _P, _P]),
+    "trajopt_debug_linesearch_rows": (_I, [_P]),
+    "trajopt_debug_linesearch": (_I, [_P, _P, _P]),
     "trajopt_debug_stage": (_I, [_P, _I, _I, _I] + [_P] * 11),
     "trajopt_debug_lie": (_I, [_I, _I, _P, _P, _P]),
     "trajopt_debug_fp64_peak": (_I, [C.c_double, C.POINTER(C.c_double), _P]),

@@ -687,6 +687,23 @@ int trajopt_debug_gains(trajopt_handle* h, double* d_k, double* d_K, void* strea
     return 0;
 }
 
+int trajopt_debug_linesearch_rows(trajopt_handle* h) {
+    if (!h || !h->have_params) return fail(TRAJOPT_E_INVALID, "trajopt_debug_linesearch_rows: handle without parameters");
+    return h->cand_rows;
+}
+
+int trajopt_debug_linesearch(trajopt_handle* h, double* d_table, void* stream) {
+    if (!h || !d_table) return fail(TRAJOPT_E_INVALID, "trajopt_debug_linesearch: NULL argument");
+    if (!h->begun) return fail(TRAJOPT_E_STATE, "trajopt_debug_linesearch: call trajopt_begin first");
+    DeviceGuard guard(h->device);
+    // source is [rows][Bp]; the export kernel writes out[b][r] for a [B][rows] target, so transpose by swapping roles:
+    // k_export_rows(B, Bp, rows, src, out) gives out[b * rows + r]; the table is documented as [rows][B], hence a 2D copy
+    CUDA_OK(cudaMemcpy2DAsync(d_table, (size_t)h->B * sizeof(double), h->w.Jcand, (size_t)h->Bp * sizeof(double),
+                              (size_t)h->B * sizeof(double), (size_t)h->cand_rows, cudaMemcpyDeviceToDevice,
+                              (cudaStream_t)stream));
+    return 0;
+}
+
 int trajopt_debug_stage(trajopt_handle* h, int i, int terminal, int n, const double* d_x, const double* d_u, double* d_f,
                         double* d_Fx, double* d_Fu, double* d_l, double* d_lx, double* d_lxx, double* d_lu, double* d_err,
                         void* stream) {
@@ -701,9 +718,9 @@ int trajopt_debug_stage(trajopt_handle* h, int i, int terminal, int n, const dou
 }
 
 int trajopt_debug_lie(int op, int n, const double* d_in, double* d_out, void* stream) {
-    if (n < 0 || !d_in || !d_out) return fail(TRAJOPT_E_INVALID, "trajopt_debug_lie: bad argument");
     if (op < 0 || op >= LIE_OP_COUNT) return fail(TRAJOPT_E_INVALID, "trajopt_debug_lie: unknown op");
     if (n == 0) return 0;
+    if (n < 0 || !d_in || !d_out) return fail(TRAJOPT_E_INVALID, "trajopt_debug_lie: bad argument");
     LAUNCH(k_debug_lie, blocks_for(n, 128), 128, 0, (cudaStream_t)stream, op, n, d_in, d_out);
     return 0;
 }

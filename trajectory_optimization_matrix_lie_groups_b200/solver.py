@@ -222,6 +222,15 @@ class BatchSolver:
         check(lib.trajopt_debug_gains(self._h, _ptr(k), _ptr(K), _stream(self.device)))
         return k, K
 
+    def debug_linesearch(self):
+        """Line-search table of the last iteration, (rows, B); see trajopt_debug_linesearch in the header."""
+        rows = lib.trajopt_debug_linesearch_rows(self._h)
+        if rows < 0:
+            check(rows)
+        t = self._new(rows, self.B)
+        check(lib.trajopt_debug_linesearch(self._h, _ptr(t), _stream(self.device)))
+        return t
+
     def stage_eval(self, i, x_rows, u_rows=None, terminal=False, want=("f", "F_x", "F_u", "l", "l_x", "l_xx", "l_u", "err")):
         """The reference's per-stage callbacks on rows of states/controls against reference row i."""
         x = torch.as_tensor(np.asarray(x_rows, dtype=np.float64)).reshape(-1, self.NS).contiguous().to(self.device)
