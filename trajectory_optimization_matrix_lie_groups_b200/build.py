@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtrajopt_b200.so")
 SOURCES = ["api.cu"]
-HEADERS = ["common.cuh", "lie.cuh", "model.cuh", "kernels.cuh", "backward.cuh", "kernels_fwd.cuh", "debug.cuh",
+HEADERS = ["common.cuh", "lie.cuh", "model.cuh", "kernels.cuh", "backward.cuh", "backward3.cuh", "kernels_fwd.cuh", "debug.cuh",
            os.path.join("..", "..", "include", "trajopt_b200.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

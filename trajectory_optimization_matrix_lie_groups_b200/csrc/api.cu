@@ -8,7 +8,10 @@
 #include <new>
 #include <vector>
 
+#include <cstdlib>
+
 #include "kernels_fwd.cuh"
+#include "backward3.cuh"
 #include "debug.cuh"
 
 using namespace trajopt;
@@ -141,9 +144,23 @@ int run_linearize(trajopt_handle* h, cudaStream_t s) {
     return 0;
 }
 
+// TRAJOPT_BACKWARD=1 selects the one-warp-per-group sweep for the 12-dimensional families too (A/B measurements)
+static bool use_one_warp_sweep() {
+    static const bool v = [] { const char* e = getenv("TRAJOPT_BACKWARD"); return e && e[0] == '1'; }();
+    return v;
+}
+
 template <int KIND, bool MS>
 int run_backward(trajopt_handle* h, cudaStream_t s, int it) {
     PhaseTimer t(h, s, PH_BWD);
+    if constexpr (KIND != TRAJOPT_SO3) {
+        if (!use_one_warp_sweep()) {
+            constexpr size_t smem3 = B3Smem<KIND>::BYTES;
+            CUDA_OK(cudaFuncSetAttribute(k_backward3<KIND, MS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+            LAUNCH((k_backward3<KIND, MS>), h->Bp / 32, kB3Threads, smem3, s, h->prm, h->w, it);
+            return 0;
+        }
+    }
     constexpr size_t smem = (size_t)bwd_smem_doubles<KIND>() * kBlock * sizeof(double);
     CUDA_OK(cudaFuncSetAttribute(k_backward<KIND, MS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     LAUNCH((k_backward<KIND, MS>), h->Bp / kBlock, kBlock, smem, s, h->prm, h->w, it);
@@ -483,6 +500,13 @@ int trajopt_set_params(trajopt_handle* h, const trajopt_params* p) {
     if (h->kind == TRAJOPT_SE3)
         for (int r = 0; r < 3; ++r) q.Bv[(3 + r) * NU + 3 + r] = q.dt / q.mass;
     if (h->kind == TRAJOPT_DRONE) q.Bv[5 * NU + 3] = q.dt / q.mass;
+    memset(q.BtB, 0, sizeof(q.BtB));
+    for (int a = 0; a < NU; ++a)
+        for (int c = 0; c < NU; ++c) {
+            double sacc = 0.0;
+            for (int r = 0; r < NV; ++r) sacc = std::fma(q.Bv[r * NU + a], q.Bv[r * NU + c], sacc);
+            q.BtB[a * NU + c] = sacc;
+        }
     for (int j = 0; j < 6; ++j) { q.lb[j] = p->lb[j]; q.ub[j] = p->ub[j]; }
     q.tol_grad = p->tol_grad_norm;
     q.tol_defect = p->tol_d_norm;

@@ -133,15 +133,15 @@ __global__ void __launch_bounds__(kBlock) k_backward(const Params prm, Work w, i
 
     // ---- terminal condition: V_x = l_x(N), V_xx = l_xx(N) --------------------------------
     {
-        const double* rec = lin + soa(N, 0, F, (int)Bp, b);
+        const double* rec = lin + lsoa(N, 0, F, N + 1, b);
 #pragma unroll
-        for (int j = 0; j < NX; ++j) Vxs[j * kBlock] = rec[(size_t)(LR::LX_OFF + j) * Bp];
+        for (int j = 0; j < NX; ++j) Vxs[j * kBlock] = rec[(size_t)(LR::LX_OFF + j) * kRecStride];
 #pragma unroll
         for (int r = 0; r < NX; ++r)
 #pragma unroll
             for (int c = r; c < NX; ++c) {
                 double v;
-                if (c < NP) v = rec[(size_t)(LR::LXX_OFF + tri_idx(NP, r, c)) * Bp];
+                if (c < NP) v = rec[(size_t)(LR::LXX_OFF + tri_idx(NP, r, c)) * kRecStride];
                 else if (r >= NP) v = 2.0 * prm.P2[(r - NP) * NV + (c - NP)];
                 else v = 0.0;
                 Vs[tri_idx(NX, r, c) * kBlock] = v;
@@ -157,28 +157,15 @@ __global__ void __launch_bounds__(kBlock) k_backward(const Params prm, Work w, i
     double gsum = 0.0;
     int flags = 0;
 
-    // B^T B (constant), upper triangle
-    double BtB[NU * NU];
-#pragma unroll
-    for (int a = 0; a < NU; ++a)
-#pragma unroll
-        for (int c = a; c < NU; ++c) {
-            double s = 0.0;
-#pragma unroll
-            for (int r = 0; r < NV; ++r)
-                if (bv_nz<KIND>(r, a) && bv_nz<KIND>(r, c)) s += prm.Bv[r * NU + a] * prm.Bv[r * NU + c];
-            BtB[a * NU + c] = s;
-        }
-
     for (int i = N - 1; i >= 0; --i) {
-        const double* __restrict__ rec = lin + soa(i, 0, F, (int)Bp, b);
+        const double* __restrict__ rec = lin + lsoa(i, 0, F, N + 1, b);
         if (i > 0) {   // pull the next record towards L2 while this stage computes
-            const char* nxt = (const char*)(lin + soa(i - 1, 0, F, (int)Bp, b - lane));
+            const char* nxt = (const char*)(lin + lsoa(i - 1, 0, F, N + 1, b - lane));
 #pragma unroll
             for (int t = 0; t < (F * 2 + kBlock - 1) / kBlock; ++t) {
                 const int line = t * kBlock + lane;
                 if (line < F * 2) {
-                    const char* p = nxt + (size_t)(line >> 1) * Bp * sizeof(double) + (size_t)(line & 1) * 128;
+                    const char* p = nxt + (size_t)line * 128;
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
                 }
             }
@@ -191,7 +178,7 @@ __global__ void __launch_bounds__(kBlock) k_backward(const Params prm, Work w, i
         if constexpr (MS) {
             double d[NX];
 #pragma unroll
-            for (int j = 0; j < NX; ++j) d[j] = rec[(size_t)(LR::D_OFF + j) * Bp];
+            for (int j = 0; j < NX; ++j) d[j] = rec[(size_t)(LR::D_OFF + j) * kRecStride];
 #pragma unroll
             for (int r = 0; r < NX; ++r)
 #pragma unroll
@@ -205,7 +192,7 @@ __global__ void __launch_bounds__(kBlock) k_backward(const Params prm, Work w, i
         // (2) Q_u = l_u + Bv^T v_vel ; gradient-norm term
         double Qu[NU], lu[NU];
 #pragma unroll
-        for (int a = 0; a < NU; ++a) lu[a] = rec[(size_t)(LR::LU_OFF + a) * Bp];
+        for (int a = 0; a < NU; ++a) lu[a] = rec[(size_t)(LR::LU_OFF + a) * kRecStride];
 #pragma unroll
         for (int a = 0; a < NU; ++a) {
             double s = lu[a];
@@ -242,7 +229,7 @@ __global__ void __launch_bounds__(kBlock) k_backward(const Params prm, Work w, i
                 double q[3], qp[3];
 #pragma unroll
                 for (int j = 0; j < 3; ++j) {
-                    q[j] = rec[(size_t)(LR::LX_OFF + CB * 3 + j) * Bp];
+                    q[j] = rec[(size_t)(LR::LX_OFF + CB * 3 + j) * kRecStride];
                     qp[j] = q[j];
                 }
                 sfor<0, NB>([&](auto rbc) {
@@ -250,7 +237,7 @@ __global__ void __launch_bounds__(kBlock) k_backward(const Params prm, Work w, i
                     constexpr int kind = blk_kind<KIND>(RB, CB);
                     if constexpr (kind != BK_ZERO) {
                         double m[9];
-                        load_blk<KIND, RB, CB>(rec, Bp, m);
+                        load_blk<KIND, RB, CB>(rec, kRecStride, m);
 #pragma unroll
                         for (int ii = 0; ii < 3; ++ii)
 #pragma unroll
@@ -296,7 +283,7 @@ __global__ void __launch_bounds__(kBlock) k_backward(const Params prm, Work w, i
 #pragma unroll
                 for (int c = a; c < NU; ++c) {
                     double s = 2.0 * prm.R[a * NU + c];
-                    if (a == c) s += rec[(size_t)(LR::LUU_OFF + a) * Bp];
+                    if (a == c) s += rec[(size_t)(LR::LUU_OFF + a) * kRecStride];
 #pragma unroll
                     for (int r = 0; r < NV; ++r)
                         if (bv_nz<KIND>(r, a)) s = fma(prm.Bv[r * NU + a], T[r * NU + c], s);
@@ -313,7 +300,7 @@ __global__ void __launch_bounds__(kBlock) k_backward(const Params prm, Work w, i
             bool pd = true;
 #pragma unroll
             for (int c = 0; c < NU; ++c) {
-                double dg = fma(mu_used, BtB[c * NU + c], Quu0[c * NU + c]);
+                double dg = fma(mu_used, prm.BtB[c * NU + c], Quu0[c * NU + c]);
 #pragma unroll
                 for (int k = 0; k < c; ++k) dg = fma(-Lc[c * NU + k], Lc[c * NU + k], dg);
                 if (!(dg > 0.0)) pd = false;
@@ -321,7 +308,7 @@ __global__ void __launch_bounds__(kBlock) k_backward(const Params prm, Work w, i
                 Lc[c * NU + c] = inv;
 #pragma unroll
                 for (int r = c + 1; r < NU; ++r) {
-                    double s = fma(mu_used, BtB[c * NU + r], Quu0[c * NU + r]);
+                    double s = fma(mu_used, prm.BtB[c * NU + r], Quu0[c * NU + r]);
 #pragma unroll
                     for (int k = 0; k < c; ++k) s = fma(-Lc[r * NU + k], Lc[c * NU + k], s);
                     Lc[r * NU + c] = s * inv;
@@ -386,7 +373,7 @@ __global__ void __launch_bounds__(kBlock) k_backward(const Params prm, Work w, i
                 constexpr int kind = blk_kind<KIND>(KB, CB);
                 if constexpr (kind != BK_ZERO) {
                     double m[9];
-                    load_blk<KIND, KB, CB>(rec, Bp, m);
+                    load_blk<KIND, KB, CB>(rec, kRecStride, m);
 #pragma unroll
                     for (int r = 0; r < NX; ++r)
 #pragma unroll
@@ -459,7 +446,7 @@ __global__ void __launch_bounds__(kBlock) k_backward(const Params prm, Work w, i
                         const int r = RB * 3 + ii, c = CB * 3 + j;
                         double s = 0.0;
                         if (r <= c) {
-                            if (c < NP) s = rec[(size_t)(LR::LXX_OFF + tri_idx(NP, r, c)) * Bp];
+                            if (c < NP) s = rec[(size_t)(LR::LXX_OFF + tri_idx(NP, r, c)) * kRecStride];
                             else if (r >= NP) s = 2.0 * prm.W2[(r - NP) * NV + (c - NP)];
                         }
                         acc[ii][j] = s;
@@ -469,7 +456,7 @@ __global__ void __launch_bounds__(kBlock) k_backward(const Params prm, Work w, i
                     constexpr int kind = blk_kind<KIND>(KB, RB);
                     if constexpr (kind != BK_ZERO) {
                         double m[9];
-                        load_blk<KIND, KB, RB>(rec, Bp, m);
+                        load_blk<KIND, KB, RB>(rec, kRecStride, m);
 #pragma unroll
                         for (int k = 0; k < 3; ++k)
 #pragma unroll

@@ -25,20 +25,24 @@ template <> struct Dims<TRAJOPT_DRONE> { static constexpr int NX = 12, NP = 6, N
 template <int KIND> struct RefRow { static constexpr int N = (KIND == TRAJOPT_SO3) ? 16 : 31; };
 
 // Per-stage linearisation record written by the stage-parallel kernel and read by the
-// backward sweep (SoA: [stage][field][problem]).  Field offsets:
-//   SE3/drone:  a(9) b(9) c(9) e(9) h11(9) h12(9) vdt(3) [s(3) drone]  then  d(12) lx(12) lxx(21) lu(NU) [luu_add(NU) AL]
-//   SO3      :  a(9) c(9) h(9)                                         then  d(6)  lx(6)  lxx(6)  lu(3)
+// backward sweep.  Layout in HBM is group-major: [group of 32 problems][stage][field][32], so the
+// record of one stage of one warp's 32 problems is ONE contiguous chunk of LEN * 256 bytes whose
+// first STAGE_LEN fields (what every warp of the backward CTA needs repeatedly) are brought into
+// shared memory by a single TMA bulk copy per stage.  Field offsets:
+//   SE3/drone:  a(9) b(9) c(9) e(9) h11(9) h12(9) vdt(3) [s(3) drone] | d(12) lu(NU) | luu_add(NU, AL) lx(12) lxx(21)
+//   SO3      :  a(9) c(9) h(9)                                        | d(6)  lu(3)  | luu_add(3)      lx(6)  lxx(6)
 template <int KIND> struct LinRec {
     using D = Dims<KIND>;
     static constexpr int A_OFF = 0;
     static constexpr int A_LEN = (KIND == TRAJOPT_SO3) ? 27 : (KIND == TRAJOPT_DRONE ? 60 : 57);
     static constexpr int D_OFF = A_OFF + A_LEN;
-    static constexpr int LX_OFF = D_OFF + D::NX;
+    static constexpr int LU_OFF = D_OFF + D::NX;
+    static constexpr int STAGE_LEN = LU_OFF + D::NU;    // prefix staged in shared memory by the backward sweep
+    static constexpr int LUU_OFF = STAGE_LEN;           // AL only: diagonal addition to l_uu
+    static constexpr int LX_OFF = LUU_OFF + D::NU;
     static constexpr int LXX_OFF = LX_OFF + D::NX;
     static constexpr int LXX_LEN = D::NP * (D::NP + 1) / 2;
-    static constexpr int LU_OFF = LXX_OFF + LXX_LEN;
-    static constexpr int LUU_OFF = LU_OFF + D::NU;      // AL only: diagonal addition to l_uu
-    static constexpr int LEN = LUU_OFF + D::NU;
+    static constexpr int LEN = LXX_OFF + LXX_LEN;
 };
 
 // ------------------------------------------------------------------------------------------
@@ -58,6 +62,7 @@ struct Params {
     double P1[36], P2[36];       // terminal weights
     double R[36];                // NU x NU
     double Bv[36];               // (NP x NU) velocity rows of f_u = Jinv * Pu * dt  (row-major, leading dim NU)
+    double BtB[36];              // Bv^T Bv (NU x NU): what mu * I adds to Q_uu (traopt_controller.py:2311-2313)
     double lb[6], ub[6];
     double tol_grad, tol_defect;
     double mu_min, mu_max, delta0;           // Levenberg-Marquardt schedule
@@ -69,6 +74,12 @@ struct Params {
 __device__ __forceinline__ size_t soa(int stage, int field, int F, int Bp, int b) {
     return ((size_t)stage * F + field) * (size_t)Bp + b;
 }
+
+// linearisation records: group-major (see LinRec); Np1 = N + 1 stages per problem
+__device__ __forceinline__ size_t lsoa(int stage, int field, int F, int Np1, int b) {
+    return ((((size_t)(b >> 5) * Np1 + stage) * F + field) << 5) + (size_t)(b & 31);
+}
+constexpr int kRecStride = 32;   // doubles between consecutive fields of one problem's record
 
 #define CUDA_OK(call)                                                      \
     do {                                                                   \

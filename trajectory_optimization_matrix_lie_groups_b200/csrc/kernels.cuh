@@ -19,7 +19,7 @@ struct Work {
     double* U[2];        // [N][NU][Bp]  x 2
     int* sel;            // [Bp] which buffer holds the current trajectory
     const double* ref;   // [N+1][RefRow]
-    double* lin;         // [N+1][LinRec::LEN][Bp]
+    double* lin;         // [Bp/32][N+1][LinRec::LEN][32] (group-major, see LinRec)
     double* Lc;          // [N+1][Bp] stage costs of the current trajectory
     double* Dsq;         // [N][Bp]   squared defect norm per stage
     double* kff;         // [N][NU][Bp]
@@ -75,13 +75,13 @@ template <> struct AMat<TRAJOPT_SO3> {
         if (r < 3) return c[3 * i + j];
         return h[3 * i + j];
     }
-    TO_DEV void load(const double* __restrict__ lin, int stage, int Bp, int b) {
+    TO_DEV void load(const double* __restrict__ lin, int stage, int Np1, int b) {
         constexpr int F = LinRec<TRAJOPT_SO3>::LEN;
 #pragma unroll
         for (int i = 0; i < 9; ++i) {
-            a[i] = lin[soa(stage, i, F, Bp, b)];
-            c[i] = lin[soa(stage, 9 + i, F, Bp, b)];
-            h[i] = lin[soa(stage, 18 + i, F, Bp, b)];
+            a[i] = lin[lsoa(stage, i, F, Np1, b)];
+            c[i] = lin[lsoa(stage, 9 + i, F, Np1, b)];
+            h[i] = lin[lsoa(stage, 18 + i, F, Np1, b)];
         }
     }
 };
@@ -109,21 +109,21 @@ template <int KIND> struct AMat {   // SE3 and DRONE
         if (bc == 2) return skew_sign(i, j) * vdt[k];
         return ((i == j) ? 1.0 : 0.0) - skew_sign(i, j) * vdt[k];
     }
-    TO_DEV void load(const double* __restrict__ lin, int stage, int Bp, int bb) {
+    TO_DEV void load(const double* __restrict__ lin, int stage, int Np1, int bb) {
         constexpr int F = LinRec<KIND>::LEN;
 #pragma unroll
         for (int i = 0; i < 9; ++i) {
-            a[i] = lin[soa(stage, i, F, Bp, bb)];
-            b[i] = lin[soa(stage, 9 + i, F, Bp, bb)];
-            c[i] = lin[soa(stage, 18 + i, F, Bp, bb)];
-            e[i] = lin[soa(stage, 27 + i, F, Bp, bb)];
-            h11[i] = lin[soa(stage, 36 + i, F, Bp, bb)];
-            h12[i] = lin[soa(stage, 45 + i, F, Bp, bb)];
+            a[i] = lin[lsoa(stage, i, F, Np1, bb)];
+            b[i] = lin[lsoa(stage, 9 + i, F, Np1, bb)];
+            c[i] = lin[lsoa(stage, 18 + i, F, Np1, bb)];
+            e[i] = lin[lsoa(stage, 27 + i, F, Np1, bb)];
+            h11[i] = lin[lsoa(stage, 36 + i, F, Np1, bb)];
+            h12[i] = lin[lsoa(stage, 45 + i, F, Np1, bb)];
         }
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-            vdt[i] = lin[soa(stage, 54 + i, F, Bp, bb)];
-            s[i] = (KIND == TRAJOPT_DRONE) ? lin[soa(stage, 57 + i, F, Bp, bb)] : 0.0;
+            vdt[i] = lin[lsoa(stage, 54 + i, F, Np1, bb)];
+            s[i] = (KIND == TRAJOPT_DRONE) ? lin[lsoa(stage, 57 + i, F, Np1, bb)] : 0.0;
         }
     }
 };
@@ -322,14 +322,14 @@ __global__ void __launch_bounds__(128) k_linearize(const Params prm, Work w) {
         }
 #pragma unroll
         for (int j = 0; j < NU; ++j) {
-            out[soa(stage, LR::LU_OFF + j, F, Bp, b)] = lu[j];
-            out[soa(stage, LR::LUU_OFF + j, F, Bp, b)] = luu_add[j];
+            out[lsoa(stage, LR::LU_OFF + j, F, prm.N + 1, b)] = lu[j];
+            out[lsoa(stage, LR::LUU_OFF + j, F, prm.N + 1, b)] = luu_add[j];
         }
         // dynamics Jacobian
         double rec[LR::A_LEN];
         dyn_jacobian<KIND>(prm, x, rec);
 #pragma unroll
-        for (int j = 0; j < LR::A_LEN; ++j) out[soa(stage, LR::A_OFF + j, F, Bp, b)] = rec[j];
+        for (int j = 0; j < LR::A_LEN; ++j) out[lsoa(stage, LR::A_OFF + j, F, prm.N + 1, b)] = rec[j];
         // defect against the next shooting node
         if constexpr (MS) {
             State<KIND> fx, xnext;
@@ -339,16 +339,16 @@ __global__ void __launch_bounds__(128) k_linearize(const Params prm, Work w) {
             defect<KIND>(fx, xnext, d);
 #pragma unroll
             for (int j = 0; j < NX; ++j) {
-                out[soa(stage, LR::D_OFF + j, F, Bp, b)] = d[j];
+                out[lsoa(stage, LR::D_OFF + j, F, prm.N + 1, b)] = d[j];
                 dsq += d[j] * d[j];
             }
             w.Dsq[(size_t)stage * Bp + b] = dsq;
         }
     }
 #pragma unroll
-    for (int j = 0; j < NX; ++j) out[soa(stage, LR::LX_OFF + j, F, Bp, b)] = lx[j];
+    for (int j = 0; j < NX; ++j) out[lsoa(stage, LR::LX_OFF + j, F, prm.N + 1, b)] = lx[j];
 #pragma unroll
-    for (int j = 0; j < LR::LXX_LEN; ++j) out[soa(stage, LR::LXX_OFF + j, F, Bp, b)] = lxx[j];
+    for (int j = 0; j < LR::LXX_LEN; ++j) out[lsoa(stage, LR::LXX_OFF + j, F, prm.N + 1, b)] = lxx[j];
     w.Lc[(size_t)stage * Bp + b] = val;
 }
 

@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(kBlock) k_forward(const Params prm, Work w, in
         if constexpr (LINEAR) {
             // step = A dx + B du (+ alpha d), pose part retracts x(i+1)
             AMat<KIND> A;
-            A.load(lin, i, Bp, b);
+            A.load(lin, i, N + 1, b);
             double st[NX];
 #pragma unroll
             for (int r = 0; r < NX; ++r) {
@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(kBlock) k_forward(const Params prm, Work w, in
                     for (int a = 0; a < NU; ++a)
                         if (bv_nz<KIND>(r - NP, a)) s += prm.Bv[(r - NP) * NU + a] * du[a];
                 }
-                if constexpr (MS) s += alpha * lin[soa(i, LR::D_OFF + r, F, Bp, b)];
+                if constexpr (MS) s += alpha * lin[lsoa(i, LR::D_OFF + r, F, N + 1, b)];
                 st[r] = s;
             }
             if constexpr (KIND == TRAJOPT_SO3) {
@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(kBlock) k_forward(const Params prm, Work w, in
                 dyn_step<KIND>(prm, x, u, fold);
                 double d[NX];
 #pragma unroll
-                for (int j = 0; j < NX; ++j) d[j] = alpha * lin[soa(i, LR::D_OFF + j, F, Bp, b)];
+                for (int j = 0; j < NX; ++j) d[j] = alpha * lin[lsoa(i, LR::D_OFF + j, F, N + 1, b)];
                 if constexpr (KIND == TRAJOPT_SO3) {
                     double qe[4], q1[4], q2[4];
                     so3_exp(d, qe);
@@ -264,15 +264,15 @@ __global__ void __launch_bounds__(kBlock) k_ms_expected(const Params prm, Work w
         // first / second order terms
         double f1 = 0.0, f2 = 0.0;
 #pragma unroll
-        for (int c = 0; c < NX; ++c) f1 += lin[soa(i, LR::LX_OFF + c, F, Bp, b)] * dx[c];
+        for (int c = 0; c < NX; ++c) f1 += lin[lsoa(i, LR::LX_OFF + c, F, N + 1, b)] * dx[c];
 #pragma unroll
-        for (int a = 0; a < NU; ++a) f1 += lin[soa(i, LR::LU_OFF + a, F, Bp, b)] * du[a];
+        for (int a = 0; a < NU; ++a) f1 += lin[lsoa(i, LR::LU_OFF + a, F, N + 1, b)] * du[a];
         // dx^T l_xx dx
 #pragma unroll
         for (int r = 0; r < NP; ++r)
 #pragma unroll
             for (int c = 0; c < NP; ++c)
-                f2 += dx[r] * lin[soa(i, LR::LXX_OFF + sym_idx(NP, r, c), F, Bp, b)] * dx[c];
+                f2 += dx[r] * lin[lsoa(i, LR::LXX_OFF + sym_idx(NP, r, c), F, N + 1, b)] * dx[c];
 #pragma unroll
         for (int r = 0; r < NV; ++r)
 #pragma unroll
@@ -283,18 +283,18 @@ __global__ void __launch_bounds__(kBlock) k_ms_expected(const Params prm, Work w
 #pragma unroll
             for (int c = 0; c < NU; ++c) {
                 double l = 2.0 * prm.R[r * NU + c];
-                if (r == c) l += lin[soa(i, LR::LUU_OFF + r, F, Bp, b)];
+                if (r == c) l += lin[lsoa(i, LR::LUU_OFF + r, F, N + 1, b)];
                 f2 += du[r] * l * du[c];
             }
         c1 += f1;
         c2 += f2;
         // propagate
         AMat<KIND> A;
-        A.load(lin, i, Bp, b);
+        A.load(lin, i, N + 1, b);
         double st[NX];
 #pragma unroll
         for (int r = 0; r < NX; ++r) {
-            double s = lin[soa(i, LR::D_OFF + r, F, Bp, b)];
+            double s = lin[lsoa(i, LR::D_OFF + r, F, N + 1, b)];
 #pragma unroll
             for (int c = 0; c < NX; ++c)
                 if (AMat<KIND>::nz(r, c)) s += A.get(r, c) * dx[c];
@@ -321,12 +321,12 @@ __global__ void __launch_bounds__(kBlock) k_ms_expected(const Params prm, Work w
     {
         double f1 = 0.0, f2 = 0.0;
 #pragma unroll
-        for (int c = 0; c < NX; ++c) f1 += lin[soa(N, LR::LX_OFF + c, F, Bp, b)] * dx[c];
+        for (int c = 0; c < NX; ++c) f1 += lin[lsoa(N, LR::LX_OFF + c, F, N + 1, b)] * dx[c];
 #pragma unroll
         for (int r = 0; r < NP; ++r)
 #pragma unroll
             for (int c = 0; c < NP; ++c)
-                f2 += dx[r] * lin[soa(N, LR::LXX_OFF + sym_idx(NP, r, c), F, Bp, b)] * dx[c];
+                f2 += dx[r] * lin[lsoa(N, LR::LXX_OFF + sym_idx(NP, r, c), F, N + 1, b)] * dx[c];
 #pragma unroll
         for (int r = 0; r < NV; ++r)
 #pragma unroll
@@ -499,20 +499,20 @@ __global__ void k_export_lin(const Params prm, Work w, double* Fx, double* Fu, d
     const double* lin = w.lin;
     if (L) L[(size_t)b * (N + 1) + i] = w.Lc[(size_t)i * Bp + b];
     if (Lx)
-        for (int c = 0; c < NX; ++c) Lx[((size_t)b * (N + 1) + i) * NX + c] = lin[soa(i, LR::LX_OFF + c, F, Bp, b)];
+        for (int c = 0; c < NX; ++c) Lx[((size_t)b * (N + 1) + i) * NX + c] = lin[lsoa(i, LR::LX_OFF + c, F, N + 1, b)];
     if (Lxx) {
         const double* W2 = (i == N) ? prm.P2 : prm.W2;
         for (int r = 0; r < NX; ++r)
             for (int c = 0; c < NX; ++c) {
                 double v = 0.0;
-                if (r < NP && c < NP) v = lin[soa(i, LR::LXX_OFF + sym_idx(NP, r, c), F, Bp, b)];
+                if (r < NP && c < NP) v = lin[lsoa(i, LR::LXX_OFF + sym_idx(NP, r, c), F, N + 1, b)];
                 else if (r >= NP && c >= NP) v = 2.0 * W2[(r - NP) * NV + (c - NP)];
                 Lxx[(((size_t)b * (N + 1) + i) * NX + r) * NX + c] = v;
             }
     }
     if (i == N) return;
     AMat<KIND> A;
-    A.load(lin, i, Bp, b);
+    A.load(lin, i, N + 1, b);
     if (Fx) {
 #pragma unroll
         for (int r = 0; r < NX; ++r)
@@ -526,9 +526,9 @@ __global__ void k_export_lin(const Params prm, Work w, double* Fx, double* Fu, d
                 Fu[(((size_t)b * N + i) * NX + r) * NU + a] = (r >= NP && bv_nz<KIND>(r - NP, a)) ? prm.Bv[(r - NP) * NU + a] : 0.0;
     }
     if (dd)
-        for (int c = 0; c < NX; ++c) dd[((size_t)b * N + i) * NX + c] = lin[soa(i, LR::D_OFF + c, F, Bp, b)];
+        for (int c = 0; c < NX; ++c) dd[((size_t)b * N + i) * NX + c] = lin[lsoa(i, LR::D_OFF + c, F, N + 1, b)];
     if (Lu)
-        for (int a = 0; a < NU; ++a) Lu[((size_t)b * N + i) * NU + a] = lin[soa(i, LR::LU_OFF + a, F, Bp, b)];
+        for (int a = 0; a < NU; ++a) Lu[((size_t)b * N + i) * NU + a] = lin[lsoa(i, LR::LU_OFF + a, F, N + 1, b)];
 }
 
 }  // namespace trajopt
