@@ -503,22 +503,27 @@ __global__ void __launch_bounds__(kB3Threads, 4) k_backward3(const Params prm, W
             while (true) {
                 mu_used = mu;
                 bool pd = true;
-#pragma unroll
-                for (int c = 0; c < NU; ++c) {
+                // (compile-time indices throughout: a rolled loop here would push Lc into local memory)
+                sfor<0, NU>([&](auto cc) {
+                    constexpr int c = decltype(cc)::value;
                     double dg = fma(mu_used, prm.BtB[c * NU + c], Quu0[c * NU + c]);
-#pragma unroll
-                    for (int k = 0; k < c; ++k) dg = fma(-Lc[c * NU + k], Lc[c * NU + k], dg);
+                    sfor<0, c>([&](auto kc) {
+                        constexpr int k = decltype(kc)::value;
+                        dg = fma(-Lc[c * NU + k], Lc[c * NU + k], dg);
+                    });
                     if (!(dg > 0.0)) pd = false;
                     const double inv = rsqrt(dg);
                     Lc[c * NU + c] = inv;
-#pragma unroll
-                    for (int r = c + 1; r < NU; ++r) {
-                        double s = fma(mu_used, prm.BtB[c * NU + r], Quu0[c * NU + r]);
-#pragma unroll
-                        for (int k = 0; k < c; ++k) s = fma(-Lc[r * NU + k], Lc[c * NU + k], s);
-                        Lc[r * NU + c] = s * inv;
-                    }
-                }
+                    sfor<c + 1, NU>([&](auto rc) {
+                        constexpr int r = decltype(rc)::value;
+                        double sacc = fma(mu_used, prm.BtB[c * NU + r], Quu0[c * NU + r]);
+                        sfor<0, c>([&](auto kc) {
+                            constexpr int k = decltype(kc)::value;
+                            sacc = fma(-Lc[r * NU + k], Lc[c * NU + k], sacc);
+                        });
+                        Lc[r * NU + c] = sacc * inv;
+                    });
+                });
                 if (!act) break;   // finished / padded lanes only keep the barriers company
                 if (!pd) {
                     delta = fmax(1.0, delta) * prm.delta0;
