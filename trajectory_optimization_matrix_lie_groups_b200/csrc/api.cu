@@ -11,7 +11,6 @@
 #include <cstdlib>
 
 #include "kernels_fwd.cuh"
-#include "backward3.cuh"
 #include "debug.cuh"
 
 using namespace trajopt;
@@ -227,7 +226,14 @@ int inner_iteration(trajopt_handle* h, cudaStream_t s) {
                 }
                 LAUNCH(k_ls_commit_ms, bgrid, 128, 0, s, h->prm, h->w, it);
             } else {
-                if ((rc = run_forward<KIND, true, true, false>(h, s, 0, 1, -2, 0))) return rc;
+                if (h->prm.rollout_linear) {
+                    if ((rc = run_forward<KIND, true, true, false>(h, s, 0, 1, -2, 0))) return rc;
+                } else {
+                    PhaseTimer t(h, s, PH_FWD);
+                    constexpr size_t fsmem = FwdSmem<KIND>::BYTES;
+                    CUDA_OK(cudaFuncSetAttribute(k_forward_ms_full<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+                    LAUNCH((k_forward_ms_full<KIND>), h->Bp / kBlock, kBlock, fsmem, s, h->prm, h->w);
+                }
                 LAUNCH(k_accept_all, bgrid, 128, 0, s, h->prm, h->w, it);
             }
         }
@@ -420,6 +426,10 @@ int trajopt_create(int kind, int method, int N, int B, int device, trajopt_handl
     A_(h->d_ref, Np1 * h->REFROW);
     A_(w.lin, Np1 * h->LEN * Bp);
     A_(w.Lc, Np1 * Bp); A_(w.Dsq, (size_t)N * Bp);
+    if (method != TRAJOPT_SS) {
+        const int gl = (kind == TRAJOPT_SO3) ? GPre<TRAJOPT_SO3>::LEN : GPre<TRAJOPT_SE3>::LEN;
+        A_(w.Gpre, (size_t)N * gl * Bp);
+    }
     A_(w.kff, (size_t)N * h->NU * Bp); A_(w.Kfb, (size_t)N * h->NU * h->NX * Bp);
     A_(w.J, Bp); A_(w.grad, Bp); A_(w.dnorm, Bp); A_(w.mu, Bp); A_(w.delta, Bp);
     A_(w.iters, Bp); A_(w.status, Bp); A_(w.ls_state, Bp);

@@ -22,6 +22,7 @@ struct Work {
     double* lin;         // [Bp/32][N+1][LinRec::LEN][32] (group-major, see LinRec)
     double* Lc;          // [N+1][Bp] stage costs of the current trajectory
     double* Dsq;         // [N][Bp]   squared defect norm per stage
+    double* Gpre;        // [N][GPre::LEN][Bp]  MS: x(i+1) Exp(d_i) f(x_i,u_i)^-1 (pose) and f(x_i,u_i).xi of the current trajectory
     double* kff;         // [N][NU][Bp]
     double* Kfb;         // [N][NU*NX][Bp]
     double* J;           // [Bp] cost of the current trajectory (J_opt)
@@ -51,6 +52,14 @@ struct Work {
 };
 
 constexpr int kBlock = 32;
+
+// What the full-step (alpha = 1) multiple-shooting rollout needs from the CURRENT trajectory at stage i
+// besides x(i), u(i): the pose G_i = q(i+1) Exp(d_q) f(x_i,u_i).q^-1 and f(x_i,u_i).xi (traopt_controller.py:2697-2718).
+// Both are independent of the rollout's recursion, so the stage-parallel linearisation forms them.
+template <int KIND> struct GPre {
+    static constexpr int NPOSE = (KIND == TRAJOPT_SO3) ? 4 : 7;
+    static constexpr int LEN = NPOSE + (Dims<KIND>::NX - Dims<KIND>::NP);
+};
 
 // ------------------------------------------------------------------------------------------
 // Structure of the dynamics Jacobian A = f_x as 3x3 blocks (zero blocks are never touched):
@@ -343,6 +352,30 @@ __global__ void __launch_bounds__(128) k_linearize(const Params prm, Work w) {
                 dsq += d[j] * d[j];
             }
             w.Dsq[(size_t)stage * Bp + b] = dsq;
+            // G_i for the alpha = 1 rollout, composed left to right exactly as k_forward does for any alpha
+            {
+                constexpr int GL = GPre<KIND>::LEN, GP = GPre<KIND>::NPOSE;
+                double* gp = w.Gpre + soa(stage, 0, GL, Bp, b);
+                if constexpr (KIND == TRAJOPT_SO3) {
+                    double qe[4], q1[4], q2[4];
+                    so3_exp(d, qe);
+                    quat_compose(xnext.q, qe, q1);
+                    quat_compose_inv_r(q1, fx.q, q2);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) gp[(size_t)j * Bp] = q2[j];
+                } else {
+                    double qe[4], pe[3], q1[4], p1[3], q2[4], p2[3];
+                    se3_exp(d, qe, pe);
+                    se3_compose(xnext.q, xnext.p, qe, pe, q1, p1);
+                    se3_compose_inv_r(q1, p1, fx.q, fx.p, q2, p2);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) gp[(size_t)j * Bp] = q2[j];
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) gp[(size_t)(4 + j) * Bp] = p2[j];
+                }
+#pragma unroll
+                for (int j = 0; j < NX - D::NP; ++j) gp[(size_t)(GP + j) * Bp] = fx.xi[j];
+            }
         }
     }
 #pragma unroll

@@ -2,6 +2,7 @@
 #pragma once
 #include "kernels.cuh"
 #include "backward.cuh"
+#include "backward3.cuh"
 
 namespace trajopt {
 
@@ -161,6 +162,131 @@ __global__ void __launch_bounds__(kBlock) k_forward(const Params prm, Work w, in
         J = J + stage_cost<KIND>(prm, xnew, nullptr, refrow, true);
         w.Jcand[(size_t)ai * Bp + b] = J;
         if (MS) w.Jcand[(size_t)(prm.n_alphas + ai) * Bp + b] = sqrt(dsq);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// The hot rollout: multiple shooting, rollout='nonlinear', full step (alpha = 1), written to the other
+// buffer, no cost (the next linearisation evaluates it).  One warp per 32 problems, the horizon runs
+// sequentially inside the thread.  Per stage the gains K_i (NU x NX), k_i and u_i of the warp's 32
+// problems are staged in shared memory, double-buffered, by TMA bulk copies issued two stages ahead
+// (one 256-byte row per field, spread over the lanes; mbarrier completion), so the recursion never
+// waits on HBM for them; G_i and f(x_i,u_i).xi come precomputed from the linearisation (GPre).
+//   dx = x_new(i) (-) x(i);  u_new = u + k + K dx;  f_new = f(x_new, u_new)
+//   q_new(i+1) = G_i f_new.q;  xi_new(i+1) = xi(i+1) + f_new.xi - f.xi + d_xi          (:2697-2718)
+// ------------------------------------------------------------------------------------------
+template <int KIND> struct FwdSmem {
+    using D = Dims<KIND>;
+    static constexpr int K_OFF = 0;
+    static constexpr int KFF_OFF = D::NU * D::NX;
+    static constexpr int U_OFF = KFF_OFF + D::NU;
+    static constexpr int FIELDS = U_OFF + D::NU;
+    static constexpr int BUF_DOUBLES = FIELDS * 32;
+    static constexpr size_t BYTES = (size_t)2 * BUF_DOUBLES * 8 + 16;
+};
+
+template <int KIND>
+__global__ void __launch_bounds__(kBlock) k_forward_ms_full(const Params prm, Work w) {
+    using D = Dims<KIND>;
+    using LR = LinRec<KIND>;
+    using FS = FwdSmem<KIND>;
+    constexpr int NX = D::NX, NP = D::NP, NU = D::NU, NV = NX - NP, F = LR::LEN, NS = D::NS;
+    constexpr int GL = GPre<KIND>::LEN, GP = GPre<KIND>::NPOSE;
+    extern __shared__ __align__(128) double fsm[];
+    const int lane = threadIdx.x;
+    const int b = blockIdx.x * kBlock + lane;
+    const int Bp = prm.Bp, N = prm.N;
+    const bool act = (b < prm.B) && (w.status[b] == TRAJOPT_RUNNING);
+    if (__ballot_sync(0xffffffffu, act) == 0u) return;
+    const int cur = w.sel[b];
+    const double* X = w.X[cur];
+    const double* U = w.U[cur];
+    double* Xn = w.X[1 - cur];
+    double* Un = w.U[1 - cur];
+    // The u rows are copied for the whole group from ONE buffer: the one the running problems use (they have
+    // all flipped once per iteration).  Should running lanes ever disagree, u is read per lane instead.
+    const unsigned actmask = __ballot_sync(0xffffffffu, act);
+    const int cur_run = __shfl_sync(0xffffffffu, cur, __ffs(actmask) - 1);
+    const bool mixed = __ballot_sync(0xffffffffu, act && cur != cur_run) != 0u;
+    const uint32_t bar0 = b3_smem_addr(fsm + 2 * FS::BUF_DOUBLES);
+    const uint32_t bar1 = bar0 + 8;
+    if (lane == 0) {
+        b3_mbar_init(bar0, 1);
+        b3_mbar_init(bar1, 1);
+    }
+    __syncwarp();
+    const int b0 = blockIdx.x * kBlock;   // first problem of the group: rows of 32 lanes are contiguous in every SoA array
+    auto issue = [&](int stage, int buf) {
+        const uint32_t dst = b3_smem_addr(fsm + buf * FS::BUF_DOUBLES);
+        const uint32_t bar = buf ? bar1 : bar0;
+        const int nf = mixed ? FS::U_OFF : FS::FIELDS;
+        if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(nf * 256) : "memory");
+        __syncwarp();
+        for (int f = lane; f < nf; f += 32) {
+            const double* src;
+            if (f < FS::KFF_OFF) src = w.Kfb + soa(stage, f, NU * NX, Bp, b0);
+            else if (f < FS::U_OFF) src = w.kff + soa(stage, f - FS::KFF_OFF, NU, Bp, b0);
+            else src = w.U[cur_run] + soa(stage, f - FS::U_OFF, NU, Bp, b0);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             dst + (uint32_t)f * 256u),
+                         "l"(src), "r"(256u), "r"(bar)
+                         : "memory");
+        }
+    };
+    issue(0, 0);
+    if (N > 1) issue(1, 1);
+
+    State<KIND> xnew, x, xnext;
+    load_state<KIND>(X, 0, Bp, b, x);
+    xnew = x;
+    if (act) store_state<KIND>(Xn, 0, Bp, b, xnew);
+    uint32_t ph0 = 0, ph1 = 0;
+    for (int i = 0; i < N; ++i) {
+        const int buf = i & 1;
+        // independent of the recursion: issue these loads first
+        load_state<KIND>(X, i + 1, Bp, b, xnext);
+        double G[GP], fxi[NV], dxi[NV];
+        {
+            const double* gp = w.Gpre + soa(i, 0, GL, Bp, b);
+#pragma unroll
+            for (int j = 0; j < GP; ++j) G[j] = gp[(size_t)j * Bp];
+#pragma unroll
+            for (int j = 0; j < NV; ++j) fxi[j] = gp[(size_t)(GP + j) * Bp];
+#pragma unroll
+            for (int j = 0; j < NV; ++j) dxi[j] = w.lin[lsoa(i, LR::D_OFF + NP + j, F, N + 1, b)];
+        }
+        double dx[NX];
+        state_minus<KIND>(xnew, x, dx);
+        if (buf) { b3_mbar_wait(bar1, ph1); ph1 ^= 1u; } else { b3_mbar_wait(bar0, ph0); ph0 ^= 1u; }
+        const double* sb = fsm + buf * FS::BUF_DOUBLES + lane;
+        double unew[NU];
+#pragma unroll
+        for (int a = 0; a < NU; ++a) {
+            // same order as k_forward: s = alpha k (alpha = 1), then += K[a][c] dx[c] for c ascending
+            double s = sb[(FS::KFF_OFF + a) * 32];
+#pragma unroll
+            for (int c = 0; c < NX; ++c) s += sb[(FS::K_OFF + a * NX + c) * 32] * dx[c];
+            const double u = mixed ? U[soa(i, a, NU, Bp, b)] : sb[(FS::U_OFF + a) * 32];
+            unew[a] = u + s;
+        }
+        __syncwarp();                       // every lane is done with this buffer
+        if (i + 2 < N) issue(i + 2, buf);
+        if (act) {
+#pragma unroll
+            for (int a = 0; a < NU; ++a) Un[soa(i, a, NU, Bp, b)] = unew[a];
+        }
+        State<KIND> fnew, xn1;
+        dyn_step<KIND>(prm, xnew, unew, fnew);
+        if constexpr (KIND == TRAJOPT_SO3) {
+            quat_compose(G, fnew.q, xn1.q);
+        } else {
+            se3_compose(G, G + 4, fnew.q, fnew.p, xn1.q, xn1.p);
+        }
+#pragma unroll
+        for (int j = 0; j < NV; ++j) xn1.xi[j] = xnext.xi[j] + fnew.xi[j] - fxi[j] + dxi[j];
+        if (act) store_state<KIND>(Xn, i + 1, Bp, b, xn1);
+        xnew = xn1;
+        x = xnext;
     }
 }
 
