@@ -111,12 +111,13 @@ def run_reference_arm(args):
     if rank != 0:
         return 0
     its = float(NOMINAL_ITERS[args.config])
+    n_it = int(os.environ.get("TRAJOPT_BENCH_CPU_ITERS", "2"))
     if args.warmup > 0:
         cpu_sample(args.config, 1, its)
     vals, desc, cores = [], "", 0
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        v, cores, desc = cpu_sample(args.config, 1, its)
+        v, cores, desc = cpu_sample(args.config, n_it, its)
         vals.append(v)
     wall = time.perf_counter() - t0
     value = statistics.mean(vals)
@@ -336,7 +337,7 @@ def run_gpu_arm(args):
                 "returns": "xs, us, J, grad, defect, iters, status" if want_traj else "J, grad, defect, iters, status"},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "fp64", "kernel": "k_backward (Riccati sweep)", "achieved": achieved, "peak": peak,
+        "roofline": {"bound": "fp64", "kernel": "k_backward3 (Riccati sweep, 2-warp CTA per 32 problems)" if wl.kind != "so3" else "k_backward (Riccati sweep)", "achieved": achieved, "peak": peak,
                      "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": traffic,
                      "peak_source": "DFMA microbenchmark run live by this bench (no FP64 entry in MEASURED_PEAKS.json)",
                      "flop_per_launch": flop_bwd / max(bwd_n, 1), "launch_ms": bwd_ms / max(bwd_n, 1), "launches": int(bwd_n),
@@ -352,7 +353,7 @@ def run_gpu_arm(args):
     }
     if world == 1 and not args.no_cpu:
         try:
-            v, cores, desc = cpu_sample_subprocess(args.config, 1, float(iters.mean()) + 1.0)
+            v, cores, desc = cpu_sample_subprocess(args.config, 3, float(iters.mean()) + 1.0)
             line["cpu_baseline"] = {"value": v, "unit": "solves/s", "cores": cores, "kind": "port", "sample": desc}
         except Exception as e:   # the baseline is context, never a reason to lose the GPU number
             line["cpu_baseline"] = {"value": None, "unit": "solves/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
