@@ -163,8 +163,13 @@ def helix_reference(N=1400, dt=0.01):
     return q_ref, np.tile(xi, (N + 1, 1))
 
 
-def se3_tracking_al_ms(B=16384, frac=0.1, N=1400):
-    """cfg 4: main_SE3ddp_tracking_exact_al_ms.py — AL multiple shooting with input bounds, helix reference."""
+def se3_tracking_al_ms(B=16384, frac=0.02, N=1400):
+    """cfg 4: main_SE3ddp_tracking_exact_al_ms.py — AL multiple shooting with input bounds, helix reference.
+
+    Perturbations are +-2 % of the sweep half-width (p +-1, th +-0.6 deg, v +-0.2): with the +-10 % of the other
+    configs a handful of problems per thousand drive the reference's penalty scheme to its cap (mu = 1e8) without
+    ever meeting tol_constr, so they run all 100 outer x 200 inner iterations (measured: 7 of 2048 problems, 260 s
+    for the batch instead of 2 s) and the benchmark would time those stragglers.  `frac=0.1` gives that stress set."""
     q_ref, xi_ref = helix_reference(N, 0.01)
     Q = np.diag([10.0, 10, 10, 1, 1, 1, 1, 1, 1, 1, 1, 1])
     rng = np.random.default_rng(SEED)
