@@ -148,6 +148,9 @@ def workload_config(args, wl):
         "perturbation": "one of 12 x0 parameters per problem, +-10% of the reference sweep half-width, seed 24234156",
         "l2": "working set (trajectories, linearisation, gains: tens of GB) far exceeds the 126 MB L2; no flush needed",
         "parallelism": f"dp{args.gpus} (independent problems, contiguous shards)",
+        "inflight": max(1, args.inflight),
+        "inflight_note": "batches in flight per GPU (own stream + host thread each); the tail of one batch's solve, where most "
+                         "problems have converged and most CTAs exit at once, overlaps the head of the next; steps complete in order",
     }
 
 
@@ -204,7 +207,7 @@ def run_gpu_arm(args):
     import numpy as np
     import torch
     import torch.distributed as dist
-    from trajectory_optimization_matrix_lie_groups_b200 import workloads, launch_count
+    from trajectory_optimization_matrix_lie_groups_b200 import workloads, launch_count, PipelinedSolver
     from trajectory_optimization_matrix_lie_groups_b200.solver import fp64_peak_tflops
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -221,35 +224,51 @@ def run_gpu_arm(args):
 
     B = args.batch
     wl = workloads.CONFIGS[args.config](B=B * world)
-    solver, x0_rows = wl.make_solver(B=B, device=dev, offset=rank * B)
+    depth = max(1, args.inflight)
+    x0_rows = wl.x0_rows[rank * B:rank * B + B]
+    pipe = PipelinedSolver(lambda: wl.make_solver(B=B, device=dev, offset=rank * B)[0], depth=depth, device=dev)
+    solver = pipe.solvers[0]
     x0_dev = torch.as_tensor(x0_rows, device=dev)
     x0_pin = torch.as_tensor(x0_rows).pin_memory()
     want_traj = not args.no_traj
-    out_pin = {"J": torch.empty(B, dtype=torch.float64).pin_memory(), "grad": torch.empty(B, dtype=torch.float64).pin_memory(),
-               "defect": torch.empty(B, dtype=torch.float64).pin_memory(),
-               "iters": torch.empty(B, dtype=torch.int32).pin_memory(), "status": torch.empty(B, dtype=torch.int32).pin_memory(),
-               "xs": torch.empty(B, wl.N + 1, solver.NS, dtype=torch.float64).pin_memory() if want_traj else None,
-               "us": torch.empty(B, wl.N, solver.NU, dtype=torch.float64).pin_memory() if want_traj else None}
-    out_np = {k: (None if v is None else v.numpy()) for k, v in out_pin.items()}
+
+    def pinned_out():
+        o = {"J": torch.empty(B, dtype=torch.float64).pin_memory(), "grad": torch.empty(B, dtype=torch.float64).pin_memory(),
+             "defect": torch.empty(B, dtype=torch.float64).pin_memory(),
+             "iters": torch.empty(B, dtype=torch.int32).pin_memory(), "status": torch.empty(B, dtype=torch.int32).pin_memory(),
+             "xs": torch.empty(B, wl.N + 1, solver.NS, dtype=torch.float64).pin_memory() if want_traj else None,
+             "us": torch.empty(B, wl.N, solver.NU, dtype=torch.float64).pin_memory() if want_traj else None}
+        return o, {k: (None if v is None else v.numpy()) for k, v in o.items()}
+    outs = [pinned_out() for _ in range(depth)]        # one set of pinned result buffers per lane
     gathered = [torch.empty(B, 5, dtype=torch.float64, device=dev) for _ in range(world)] if world > 1 else None
 
-    def step_device():
-        out = solver.solve(x0_dev, trajectories=False)
+    def gather(out):
         if world > 1:   # the one collective of the path: per-problem summaries to every rank
             summ = torch.stack((out["J"], out["grad"], out["defect"], out["iters"].double(), out["status"].double()), dim=1)
             dist.all_gather(gathered, summ)
-        return out
 
-    def step_host():
-        return solver.solve_host(x0_pin.numpy(), trajectories=want_traj, out=out_np)
+    def run_steps(n, host):
+        """n steps, `depth` batches in flight; steps complete (and are gathered) in submission order."""
+        futs = []
+        for k in range(n):
+            if host:
+                futs.append(pipe.submit(x0_pin.numpy(), trajectories=want_traj, host=True, out=outs[k % depth][1]))
+            else:
+                futs.append(pipe.submit(x0_dev, trajectories=False))
+        last = None
+        for f in futs:
+            last = f.result()
+            if not host:
+                gather(last)
+        return last
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for _ in range(max(args.warmup, 0)):
-        out = step_device()
+    if args.warmup > 0:
+        out = run_steps(args.warmup, False)
     barrier()
 
     sampler = ClockSampler(torch.cuda.current_device() if os.environ.get("CUDA_VISIBLE_DEVICES") is None else local) if rank == 0 else None
@@ -258,8 +277,7 @@ def run_gpu_arm(args):
     t_lo = time.perf_counter()
     barrier()
     e0.record()
-    for _ in range(args.steps):
-        out = step_device()
+    out = run_steps(args.steps, False)      # every lane synchronises its stream before its result is handed back
     e1.record()
     barrier()
     t_hi = time.perf_counter()
@@ -275,23 +293,34 @@ def run_gpu_arm(args):
     Jfin = out["J"].cpu().numpy()
 
     # ---- end to end through the host-buffer C-ABI call --------------------------------------
-    step_host()
+    run_steps(min(depth, 2), True)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_host()
+    run_steps(args.steps, True)
     barrier()
     e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     h2d = x0_rows.nbytes
+    out_np = outs[(args.steps - 1) % depth][1]
     d2h = sum(v.nbytes for v in out_np.values() if v is not None)
     assert np.array_equal(out_np["iters"], iters), "host-buffer path and device path disagree"
+
+    # ---- one batch alone (no overlap): latency of a step, and the serial throughput for comparison ----
+    barrier()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    out1 = solver.solve(x0_dev, trajectories=False)
+    s1.record()
+    torch.cuda.synchronize(dev)
+    serial_ms = s0.elapsed_time(s1)
+    assert np.array_equal(out1["iters"].cpu().numpy(), iters) and np.array_equal(out1["J"].cpu().numpy(), Jfin), \
+        "pipelined and serial solves disagree"
 
     # ---- per-phase device time of one profiled step (event pairs around every launch) -------
     solver.set_profiling(True)
     solver.phase_times(reset=True)
-    step_device()
+    solver.solve(x0_dev, trajectories=False)
     torch.cuda.synchronize(dev)
     phases = solver.phase_times(reset=True)
     solver.set_profiling(False)
@@ -346,6 +375,8 @@ def run_gpu_arm(args):
                            "hbm_frac": bytes_step / step_s / 1e9 / hbm_peak, "hbm_peak_gbs": hbm_peak,
                            "hbm_peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback",
                            "algorithmic_gflop_per_step": flop_step / 1e9, "algorithmic_gb_per_step": bytes_step / 1e9},
+        "single_batch": {"ms": serial_ms, "solves_per_s": B / (serial_ms * 1e-3),
+                         "note": "one batch alone on the GPU (nothing else in flight): step latency / serial throughput"},
         "phases_ms": {"linearize": lin_ms, "backward": bwd_ms, "forward": fwd_ms, "other": oth_ms,
                       "launches": {"linearize": int(lin_n), "backward": int(bwd_n), "forward": int(fwd_n)}},
         "solve_stats": {"iters_mean": float(iters.mean()), "iters_min": int(iters.min()), "iters_max": int(iters.max()),
@@ -377,6 +408,7 @@ def main():
     ap.add_argument("--batch", type=int, default=None, help="problems per GPU")
     ap.add_argument("--no-traj", action="store_true", help="e2e leg returns only the per-problem summaries")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--inflight", type=int, default=2, help="batches in flight per GPU (1 = strictly one after the other)")
     args = ap.parse_args()
     if args.batch is None:
         args.batch = {1: 1, 2: 1024, 3: 16384, 4: 2048, 5: 131072}[args.config]

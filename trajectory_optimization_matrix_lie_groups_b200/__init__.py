@@ -6,5 +6,6 @@ requires the built CUDA library (see build.py); there is no CPU fallback.
 """
 from ._lib import TrajoptError, LIB_PATH  # noqa: F401
 from .solver import BatchSolver, lie_op, launch_count  # noqa: F401
+from .pipeline import PipelinedSolver  # noqa: F401
 
-__all__ = ["BatchSolver", "TrajoptError", "lie_op", "launch_count", "LIB_PATH"]
+__all__ = ["BatchSolver", "PipelinedSolver", "TrajoptError", "lie_op", "launch_count", "LIB_PATH"]
