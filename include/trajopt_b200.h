@@ -44,7 +44,8 @@
 extern "C" {
 #endif
 
-enum { TRAJOPT_SO3 = 0, TRAJOPT_SE3 = 1, TRAJOPT_DRONE = 2 };
+/* TRAJOPT_RIGID: RigidBodyDynamics (traopt_dynamics.py:901-1206) = SE3 + gravity, 6 inputs */
+enum { TRAJOPT_SO3 = 0, TRAJOPT_SE3 = 1, TRAJOPT_DRONE = 2, TRAJOPT_RIGID = 3 };
 enum { TRAJOPT_SS = 0, TRAJOPT_MS = 1, TRAJOPT_AL_MS = 2 };
 
 /* per-problem status (low 4 bits) and flags */
@@ -70,7 +71,7 @@ typedef struct trajopt_params {
     double dt;
     double Ib[9];            /* body inertia, J[0:3,0:3] (traopt_dynamics.py:662)                       */
     double mass;             /* J[4,4] (traopt_dynamics.py:663)                                        */
-    double gravity;          /* DroneDynamics._g = 9.8 (traopt_dynamics.py:1245); ignored otherwise    */
+    double gravity;          /* DroneDynamics / RigidBodyDynamics _g = 9.8 (:1245, :936); ignored otherwise */
     double Q[144];           /* stage weight  [NX][NX]; only the two diagonal NPxNP blocks are read    */
     double P[144];           /* terminal weight [NX][NX]                                               */
     double R[36];            /* control weight [NU][NU]                                                */

@@ -133,6 +133,28 @@ class SE3Dynamics:
         return self._Bt * self.dt                                           # :839-850
 
 
+class RigidBodyDynamics(SE3Dynamics):
+    """traopt_dynamics.py:901-1206: SE3 + gravity, inputs act on all six twist components."""
+    action_size = 6
+
+    def __init__(self, J, dt):
+        self.g = 9.8                                                        # :936
+        super().__init__(J, dt)
+
+    def _force(self, q_quat, u):
+        """:1066-1072: [0; m g R^T (-e3)] + u."""
+        down = np.array([0.0, 0.0, -1.0])
+        g_acc = self.m * self.g * (lie.quat_to_rot(q_quat).T @ down)
+        return np.concatenate((np.zeros(3), g_acc)) + u
+
+    def _f_x_lower_left(self, q_quat):
+        """:1110-1134: the same gravity block as the quadrotor, also without the m*g factor."""
+        down = np.array([0.0, 0.0, -1.0])
+        J_xi_q = np.zeros((6, 6))
+        J_xi_q[3:, :3] = lie.skew(lie.quat_to_rot(q_quat).T @ down)
+        return (self.Jinv @ J_xi_q) * self.dt
+
+
 class DroneDynamics(SE3Dynamics):
     """traopt_dynamics.py:1209-1530: SE3 + gravity + 4->6 input map."""
     action_size = 4

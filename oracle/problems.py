@@ -12,6 +12,12 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file
 
 
 def load_golden(name):
+    """`rigid_*` = the SE3 fixture of the same name re-labelled as a rigid body under gravity (the reference
+    ships no result file for RigidBodyDynamics; such problems are checked against the oracle only)."""
+    if name.startswith("rigid_"):
+        g = load_golden("se3_" + name[len("rigid_"):])
+        g["kind"] = np.array("rigid")
+        return g
     with np.load(os.path.join(GOLDEN_DIR, name + ".npz")) as z:
         return {k: z[k] for k in z.files}
 
@@ -20,6 +26,9 @@ def build(kind, J, dt, Q, R, P, q_ref, xi_ref):
     """Return (dynamics, cost, group, q_ref in the group's pose type)."""
     if kind == "se3":
         return (models.SE3Dynamics(J, dt), models.SE3TrackingQuadraticGaussNewtonCost(Q, R, P, q_ref, xi_ref),
+                solvers.SE3Group, [np.asarray(T, dtype=float) for T in q_ref])
+    if kind == "rigid":
+        return (models.RigidBodyDynamics(J, dt), models.SE3TrackingQuadraticGaussNewtonCost(Q, R, P, q_ref, xi_ref),
                 solvers.SE3Group, [np.asarray(T, dtype=float) for T in q_ref])
     if kind == "drone":
         return (models.DroneDynamics(J, dt), models.SE3TrackingQuadraticGaussNewtonCost(Q, R, P, q_ref, xi_ref),

@@ -24,7 +24,7 @@ def _rel(a, b):
 
 @pytest.mark.parametrize("name,method,horizon", [
     ("se3_n120", "ms", None), ("se3_n120", "ss", None), ("so3_n249", "ms", 40), ("so3_n249", "ss", 40),
-    ("drone_n150", "ms", 40), ("drone_n150", "ss", 40),
+    ("drone_n150", "ms", 40), ("drone_n150", "ss", 40), ("rigid_n120", "ms", 40),
 ])
 def test_linearization_matches_oracle(name, method, horizon):
     g = problems.load_golden(name)
@@ -80,7 +80,7 @@ def test_backward_gains_match_oracle(name, method):
         assert float(mu_gpu[b]) == r.mu_hist[0]
 
 
-@pytest.mark.parametrize("name", ["se3_n120", "drone_n150", "so3_n249"])
+@pytest.mark.parametrize("name", ["se3_n120", "drone_n150", "so3_n249", "rigid_n120"])
 def test_dropin_class_callbacks_match_oracle(name):
     """The mirror classes' f / f_x / f_u / l / l_x / l_xx / _err are the CUDA library's numbers."""
     from trajectory_optimization_matrix_lie_groups_b200.traoptlibrary import traopt_cost, traopt_dynamics
@@ -96,6 +96,9 @@ def test_dropin_class_callbacks_match_oracle(name):
     elif kind == "drone":
         dyn = traopt_dynamics.DroneDynamics(J, dt)
         cost = traopt_cost.SE3TrackingQuadraticGaussNewtonCost(Q, R, P, g["prob_q_ref"], xi_ref, action_size=4)
+    elif kind == "rigid":
+        dyn = traopt_dynamics.RigidBodyDynamics(J, dt)
+        cost = traopt_cost.SE3TrackingQuadraticGaussNewtonCost(Q, R, P, g["prob_q_ref"], xi_ref)
     else:
         dyn = traopt_dynamics.SE3Dynamics(J, dt)
         cost = traopt_cost.SE3TrackingQuadraticGaussNewtonCost(Q, R, P, g["prob_q_ref"], xi_ref)

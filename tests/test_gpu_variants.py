@@ -82,6 +82,9 @@ def _compare(kind, out, hist, b, r, check_alpha=True):
     ("drone_n150", "ms", 30, 6, {}),
     ("drone_n150", "ss", 30, 6, {}),
     ("drone_n150", "ms", 30, 8, {"line_search": True}),
+    ("rigid_n120", "ms", 30, 6, {}),
+    ("rigid_n120", "ss", 12, 6, {}),      # (free fall over 30 stages of 0.05 s runs into the give-up branch)
+    ("rigid_n120", "ms", 30, 6, {"rollout": "linear"}),
 ], ids=lambda v: str(v).replace(" ", "") if not isinstance(v, dict) else ",".join(f"{k}={x}" for k, x in v.items()) or "default")
 def test_batch_against_oracle(name, method, horizon, n_iter, kw):
     g = problems.load_golden(name)

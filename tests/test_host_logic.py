@@ -135,3 +135,31 @@ def test_reference_arm_and_cpu_sample_smoke():
     assert line["impl"] == "reference" and line["unit"] == "solves/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] == 2
     assert line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_reference_file_formats_roundtrip(tmp_path):
+    """Reference trajectories (.npy triplets) and result pickles in the reference's own layouts."""
+    import pickle
+    from trajectory_optimization_matrix_lie_groups_b200 import io as tio
+    q, xi = workloads.helix_reference(20, 0.01)
+    p = tmp_path / "ref.npy"
+    tio.save_reference_trajectory(p, q, xi, 0.01)
+    with open(p, "rb") as f:                      # exactly how the reference scripts read it
+        q2 = np.load(f); xi2 = np.load(f); dt2 = np.load(f)
+    assert np.array_equal(q2, q) and np.array_equal(xi2, xi) and float(dt2) == 0.01
+    q3, xi3, dt3 = tio.load_reference_trajectory(p)
+    assert np.array_equal(q3, q) and dt3 == 0.01
+    tio.save_reference_trajectory(p, q, xi)       # the variant without dt
+    assert tio.load_reference_trajectory(p)[2] is None
+    with pytest.raises(ValueError):
+        tio.save_reference_trajectory(p, q[:, :3, :2], xi)
+        tio.load_reference_trajectory(p)
+    prob = dict(J=np.eye(6), dt=0.01, q_ref=q, xi_ref=xi, x0=[q[0], xi[0]], Q=np.eye(12), P=np.eye(12), R=np.eye(6))
+    run = dict(xs=[[q[i], xi[i]] for i in range(21)], us=np.zeros((20, 6)), J_hist=[3.0, 2.0], grad_hist=[1.0, 0.5],
+               defect_hist=[1.0, 1e-14, 1e-14])
+    f = tmp_path / "res.pkl"
+    tio.save_results_pickle(f, prob, ms_se3=run, ss_se3={k: v for k, v in run.items() if k != "defect_hist"})
+    d = pickle.load(open(f, "rb"))
+    assert set(d) == {"prob", "ms_se3", "ss_se3"} and set(d["prob"]) == {"J", "dt", "q_ref", "xi_ref", "x0", "Q", "P", "R"}
+    assert len(d["ms_se3"]["xs"]) == 21 and np.array_equal(d["ms_se3"]["xs"][3][0], q[3])
+    assert "defect_hist" not in d["ss_se3"] and d["ms_se3"]["J_hist"] == [3.0, 2.0]

@@ -354,7 +354,8 @@ int debug_stage_impl(trajopt_handle* h, int i, int terminal, int n, const double
 #define DISPATCH_KIND(h, fn, ...)                                             \
     ((h)->kind == TRAJOPT_SO3   ? fn<TRAJOPT_SO3>(__VA_ARGS__)                \
      : (h)->kind == TRAJOPT_SE3 ? fn<TRAJOPT_SE3>(__VA_ARGS__)                \
-                                : fn<TRAJOPT_DRONE>(__VA_ARGS__))
+     : (h)->kind == TRAJOPT_DRONE ? fn<TRAJOPT_DRONE>(__VA_ARGS__)            \
+                                  : fn<TRAJOPT_RIGID>(__VA_ARGS__))
 
 int ensure_hist(trajopt_handle* h) {
     const int cap = h->prm.max_iters;
@@ -400,7 +401,7 @@ int64_t trajopt_launch_count(int reset) {
 int trajopt_create(int kind, int method, int N, int B, int device, trajopt_handle** out) {
     if (!out) return fail(TRAJOPT_E_INVALID, "trajopt_create: out is NULL");
     *out = nullptr;
-    if (kind < TRAJOPT_SO3 || kind > TRAJOPT_DRONE) return fail(TRAJOPT_E_INVALID, "trajopt_create: unknown problem kind");
+    if (kind < TRAJOPT_SO3 || kind > TRAJOPT_RIGID) return fail(TRAJOPT_E_INVALID, "trajopt_create: unknown problem kind");
     if (method < TRAJOPT_SS || method > TRAJOPT_AL_MS) return fail(TRAJOPT_E_INVALID, "trajopt_create: unknown method");
     if (N < 1 || N > 65534 || B < 1) return fail(TRAJOPT_E_INVALID, "trajopt_create: need 1 <= N <= 65534 and B >= 1");
     if (method == TRAJOPT_AL_MS && kind == TRAJOPT_SO3)
@@ -415,7 +416,8 @@ int trajopt_create(int kind, int method, int N, int B, int device, trajopt_handl
     h->Bp = (B + kBlock - 1) / kBlock * kBlock;
     if (kind == TRAJOPT_SO3) { h->NX = 6; h->NP = 3; h->NU = 3; h->NS = 7; h->LEN = LinRec<TRAJOPT_SO3>::LEN; h->REFROW = RefRow<TRAJOPT_SO3>::N; }
     else if (kind == TRAJOPT_SE3) { h->NX = 12; h->NP = 6; h->NU = 6; h->NS = 13; h->LEN = LinRec<TRAJOPT_SE3>::LEN; h->REFROW = RefRow<TRAJOPT_SE3>::N; }
-    else { h->NX = 12; h->NP = 6; h->NU = 4; h->NS = 13; h->LEN = LinRec<TRAJOPT_DRONE>::LEN; h->REFROW = RefRow<TRAJOPT_DRONE>::N; }
+    else if (kind == TRAJOPT_DRONE) { h->NX = 12; h->NP = 6; h->NU = 4; h->NS = 13; h->LEN = LinRec<TRAJOPT_DRONE>::LEN; h->REFROW = RefRow<TRAJOPT_DRONE>::N; }
+    else { h->NX = 12; h->NP = 6; h->NU = 6; h->NS = 13; h->LEN = LinRec<TRAJOPT_RIGID>::LEN; h->REFROW = RefRow<TRAJOPT_RIGID>::N; }
     const size_t Bp = h->Bp, Np1 = (size_t)N + 1;
     Work& w = h->w;
     int rc = 0;
@@ -507,7 +509,7 @@ int trajopt_set_params(trajopt_handle* h, const trajopt_params* p) {
     // velocity rows of f_u = J^-1 Pu dt  (traopt_dynamics.py:311-313, 668-670, 1256-1258)
     for (int r = 0; r < 3; ++r)
         for (int c = 0; c < 3; ++c) q.Bv[r * NU + c] = q.Ibinv[3 * r + c] * q.dt;
-    if (h->kind == TRAJOPT_SE3)
+    if (h->kind == TRAJOPT_SE3 || h->kind == TRAJOPT_RIGID)
         for (int r = 0; r < 3; ++r) q.Bv[(3 + r) * NU + 3 + r] = q.dt / q.mass;
     if (h->kind == TRAJOPT_DRONE) q.Bv[5 * NU + 3] = q.dt / q.mass;
     memset(q.BtB, 0, sizeof(q.BtB));

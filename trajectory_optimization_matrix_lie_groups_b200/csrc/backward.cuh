@@ -43,7 +43,7 @@ enum { BK_ZERO = 0, BK_DENSE = 1, BK_SKEW = 2, BK_IMSKEW = 3 };
 // kind and record offset of the 3x3 block (rb, cb) of A
 template <int KIND> __host__ __device__ constexpr int blk_kind(int rb, int cb) {
     if (KIND == TRAJOPT_SO3) return (rb == 1 && cb == 0) ? BK_ZERO : BK_DENSE;
-    if (cb == 0) return (rb == 0 || rb == 1) ? BK_DENSE : ((rb == 3 && KIND == TRAJOPT_DRONE) ? BK_SKEW : BK_ZERO);
+    if (cb == 0) return (rb == 0 || rb == 1) ? BK_DENSE : ((rb == 3 && has_gravity(KIND)) ? BK_SKEW : BK_ZERO);
     if (cb == 1) return rb == 1 ? BK_DENSE : BK_ZERO;
     if (cb == 2) return rb == 3 ? BK_SKEW : BK_DENSE;
     return rb == 0 ? BK_ZERO : (rb == 3 ? BK_IMSKEW : BK_DENSE);

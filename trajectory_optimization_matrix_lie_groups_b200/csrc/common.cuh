@@ -18,6 +18,10 @@ template <int KIND> struct Dims;
 template <> struct Dims<TRAJOPT_SO3>   { static constexpr int NX = 6,  NP = 3, NU = 3, NS = 7;  };
 template <> struct Dims<TRAJOPT_SE3>   { static constexpr int NX = 12, NP = 6, NU = 6, NS = 13; };
 template <> struct Dims<TRAJOPT_DRONE> { static constexpr int NX = 12, NP = 6, NU = 4, NS = 13; };
+template <> struct Dims<TRAJOPT_RIGID> { static constexpr int NX = 12, NP = 6, NU = 6, NS = 13; };
+
+// gravity acts on the body (quadrotor, rigid body): f gets m g R^T(-e3), f_x a lower-left skew block
+__host__ __device__ constexpr bool has_gravity(int kind) { return kind == TRAJOPT_DRONE || kind == TRAJOPT_RIGID; }
 
 // Doubles per reference-trajectory row (shared by the whole batch, read with uniform loads):
 //   SE3/drone: q_ref quat(4) p_ref(3) xi_ref(6) R_ref(9) [p_ref]x R_ref (9)            = 31
@@ -34,7 +38,7 @@ template <int KIND> struct RefRow { static constexpr int N = (KIND == TRAJOPT_SO
 template <int KIND> struct LinRec {
     using D = Dims<KIND>;
     static constexpr int A_OFF = 0;
-    static constexpr int A_LEN = (KIND == TRAJOPT_SO3) ? 27 : (KIND == TRAJOPT_DRONE ? 60 : 57);
+    static constexpr int A_LEN = (KIND == TRAJOPT_SO3) ? 27 : (has_gravity(KIND) ? 60 : 57);
     static constexpr int D_OFF = A_OFF + A_LEN;
     static constexpr int LU_OFF = D_OFF + D::NX;
     static constexpr int STAGE_LEN = LU_OFF + D::NU;    // prefix staged in shared memory by the backward sweep

@@ -103,7 +103,7 @@ template <int KIND> struct AMat {   // SE3 and DRONE
         if (br == 1) return true;
         if (br == 2) return bc >= 2;
         // br == 3
-        if (bc == 0) return KIND == TRAJOPT_DRONE && i != j;
+        if (bc == 0) return has_gravity(KIND) && i != j;
         if (bc == 1) return false;
         if (bc == 2) return i != j;
         return true;
@@ -132,7 +132,7 @@ template <int KIND> struct AMat {   // SE3 and DRONE
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
             vdt[i] = lin[lsoa(stage, 54 + i, F, Np1, bb)];
-            s[i] = (KIND == TRAJOPT_DRONE) ? lin[lsoa(stage, 57 + i, F, Np1, bb)] : 0.0;
+            s[i] = has_gravity(KIND) ? lin[lsoa(stage, 57 + i, F, Np1, bb)] : 0.0;
         }
     }
 };
@@ -140,7 +140,7 @@ template <int KIND> struct AMat {   // SE3 and DRONE
 // Velocity rows of f_u: Bv = Jinv Pu dt  (NV x NU), compile-time sparsity
 template <int KIND> __host__ __device__ constexpr bool bv_nz(int r, int c) {
     if (KIND == TRAJOPT_SO3) return true;
-    if (KIND == TRAJOPT_SE3) return (r < 3 && c < 3) || (r >= 3 && r == c);
+    if (KIND == TRAJOPT_SE3 || KIND == TRAJOPT_RIGID) return (r < 3 && c < 3) || (r >= 3 && r == c);
     return (r < 3 && c < 3) || (r == 5 && c == 3);   // drone: torques + body-z thrust
 }
 

@@ -108,14 +108,19 @@ TO_DEV void dyn_step(const Params& prm, const State<KIND>& x, const double* u, S
         mv3(prm.Ib, w, Jw);
         cross3(w, Jw, c1);
         cross3(w, v, c2);
-        if constexpr (KIND == TRAJOPT_DRONE) {
-            // F = [tau_u ; (0,0,f_z) + m g R^T (-e3)]               (:1393-1399, Pu :1250-1254)
+        if constexpr (has_gravity(KIND)) {
+            // drone: F = [tau_u ; (0,0,f_z) + m g R^T (-e3)]        (:1393-1399, Pu :1250-1254)
+            // rigid: F = [u_w   ; u_v       + m g R^T (-e3)]        (:1066-1072)
             const double down[3] = {0.0, 0.0, -1.0};
             double gb[3];
             quat_rotate_inv(x.q, down, gb);
             const double mg = prm.mass * prm.grav;
             fw[0] = u[0]; fw[1] = u[1]; fw[2] = u[2];
-            fv[0] = mg * gb[0]; fv[1] = mg * gb[1]; fv[2] = mg * gb[2] + u[3];
+            if constexpr (KIND == TRAJOPT_DRONE) {
+                fv[0] = mg * gb[0]; fv[1] = mg * gb[1]; fv[2] = mg * gb[2] + u[3];
+            } else {
+                fv[0] = mg * gb[0] + u[3]; fv[1] = mg * gb[1] + u[4]; fv[2] = mg * gb[2] + u[5];
+            }
         } else {
             fw[0] = u[0]; fw[1] = u[1]; fw[2] = u[2];
             fv[0] = u[3]; fv[1] = u[4]; fv[2] = u[5];
@@ -384,8 +389,8 @@ TO_DEV void dyn_jacobian(const Params& prm, const State<KIND>& x, double* rec) {
             rec[45 + i] = md * H12[i];                                 // h12
         }
         rec[54] = v[0] * dt; rec[55] = v[1] * dt; rec[56] = v[2] * dt; // vdt: h21 = vdt^, h22 = I - vdt^
-        if constexpr (KIND == TRAJOPT_DRONE) {
-            // A21 = J^-1 [[0,0],[s(R^T(-e3)),0]] dt, WITHOUT m g      (QUIRK 2, :1445-1458)
+        if constexpr (has_gravity(KIND)) {
+            // A21 = J^-1 [[0,0],[s(R^T(-e3)),0]] dt, WITHOUT m g      (QUIRK 2, :1445-1458; rigid body :1121-1134)
             const double down[3] = {0.0, 0.0, -1.0};
             double gb[3];
             quat_rotate_inv(x.q, down, gb);

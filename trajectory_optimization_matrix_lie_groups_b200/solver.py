@@ -11,10 +11,10 @@ import torch
 from . import _lib
 from ._lib import lib, check
 
-KINDS = {"so3": _lib.SO3, "se3": _lib.SE3, "drone": _lib.DRONE}
+KINDS = {"so3": _lib.SO3, "se3": _lib.SE3, "drone": _lib.DRONE, "rigid": _lib.RIGID}
 METHODS = {"ss": _lib.SS, "ms": _lib.MS, "al_ms": _lib.AL_MS}
 DIMS = {  # kind -> (NX, NP, NU, NS)
-    "so3": (6, 3, 3, 7), "se3": (12, 6, 6, 13), "drone": (12, 6, 4, 13),
+    "so3": (6, 3, 3, 7), "se3": (12, 6, 6, 13), "drone": (12, 6, 4, 13), "rigid": (12, 6, 6, 13),
 }
 
 
@@ -29,7 +29,7 @@ def _stream(device):
 class BatchSolver:
     """B independent tracking problems of one family, solved together on one GPU.
 
-    kind: 'so3' | 'se3' | 'drone';  method: 'ss' | 'ms' | 'al_ms'.
+    kind: 'so3' | 'se3' | 'drone' | 'rigid';  method: 'ss' | 'ms' | 'al_ms'.
     """
 
     def __init__(self, kind, method, N, B, device=None):

@@ -1,6 +1,7 @@
 """Dynamics classes with the reference's interface (traoptlibrary/traopt_dynamics.py).
 
-`SO3Dynamics` (:275-418), `SE3Dynamics` (:629-898) and `DroneDynamics` (:1209-1530) carry the
+`SO3Dynamics` (:275-418), `SE3Dynamics` (:629-898), `RigidBodyDynamics` (:901-1206) and `DroneDynamics`
+(:1209-1530) carry the
 inertia / time step the controllers pack into the native solver.  Their per-stage callbacks
 `f`, `f_x`, `f_u` are evaluated by the CUDA library (trajopt_debug_stage) — there is no NumPy
 implementation here.
@@ -126,6 +127,18 @@ class SE3Dynamics(_NativeDynamics):
 
     Ib = property(lambda self: self._Ib)
     m = property(lambda self: self._m)
+
+
+class RigidBodyDynamics(SE3Dynamics):
+    """Rigid body on SE(3) under gravity, 6 inputs (traopt_dynamics.py:901-1206)."""
+    KIND = "rigid"
+
+    def __init__(self, J, dt, integration_method="euler", state_size=(6, 6), action_size=6, hessians=False,
+                 debug=None, **kwargs):
+        super().__init__(J, dt, integration_method, state_size, action_size, hessians, debug)
+        self._g = 9.8                                         # :936
+
+    g = property(lambda self: self._g)
 
 
 class DroneDynamics(SE3Dynamics):
