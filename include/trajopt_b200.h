@@ -44,8 +44,9 @@
 extern "C" {
 #endif
 
-/* TRAJOPT_RIGID: RigidBodyDynamics (traopt_dynamics.py:901-1206) = SE3 + gravity, 6 inputs */
-enum { TRAJOPT_SO3 = 0, TRAJOPT_SE3 = 1, TRAJOPT_DRONE = 2, TRAJOPT_RIGID = 3 };
+/* TRAJOPT_RIGID: RigidBodyDynamics (traopt_dynamics.py:901-1206) = SE3 + gravity, 6 inputs
+ * TRAJOPT_PEND:  Pendulum3dDyanmics (traopt_dynamics.py:421-626) = SO3 + gravity torque, pivot-force input */
+enum { TRAJOPT_SO3 = 0, TRAJOPT_SE3 = 1, TRAJOPT_DRONE = 2, TRAJOPT_RIGID = 3, TRAJOPT_PEND = 4 };
 enum { TRAJOPT_SS = 0, TRAJOPT_MS = 1, TRAJOPT_AL_MS = 2 };
 
 /* per-problem status (low 4 bits) and flags */
@@ -88,6 +89,7 @@ typedef struct trajopt_params {
     /* augmented Lagrangian outer loop (traopt_controller.py:3182-3184, 3218-3221) */
     int32_t n_al_iters;
     double al_mu0, al_mu_scale, al_mu_max, tol_constr;
+    double length;           /* Pendulum3dDyanmics length of the stick (traopt_dynamics.py:459); ignored otherwise */
 } trajopt_params;
 
 const char* trajopt_last_error(void);

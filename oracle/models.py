@@ -74,6 +74,45 @@ class SO3Dynamics:
         return self._Bt * self.dt                                           # :402-403
 
 
+class Pendulum3dDynamics(SO3Dynamics):
+    """traopt_dynamics.py:421-626: 3-D pendulum, gravity torque + force input at the pivot."""
+
+    def __init__(self, J, m, length, dt):
+        super().__init__(J, dt)
+        self.m, self.l, self.g = float(m), float(length), 9.8               # :458-460
+
+    def _rho(self):
+        return self.l / 2 * np.array([0.0, 0.0, -1.0])                      # :524
+
+    def f(self, x, u, i):
+        """fd_euler :520-541."""
+        q, w = x
+        down = np.array([0.0, 0.0, -1.0])
+        Rt = lie.quat_to_rot(q).T
+        g_term = lie.skew(self.m * self.g * self._rho()) @ (Rt @ down)       # smallAdj of an SO3 tangent = skew
+        M = lie.skew(self.m * self._rho()) @ (Rt @ np.asarray(u, dtype=float))
+        qn = lie.quat_normalize(lie.quat_mul(q, lie.so3_exp(w * self.dt)))
+        wn = w + self.Jinv @ (lie.skew(w).T @ self.J @ w + g_term + M) * self.dt
+        return [qn, wn]
+
+    def f_x(self, x, u, i):
+        """:543-583.  d(R^T v)/dR = skew(R^T v) for a right perturbation of R (act and inverse Jacobians of manif)."""
+        q, w = x
+        A = super().f_x(x, u, i)
+        down = np.array([0.0, 0.0, -1.0])
+        Rt = lie.quat_to_rot(q).T
+        L1 = lie.skew(self.m * self.g * self._rho()) @ lie.skew(Rt @ down)
+        L2 = lie.skew(self.m * self._rho()) @ lie.skew(Rt @ np.asarray(u, dtype=float))
+        A[3:, :3] = self.Jinv @ (L1 + L2) * self.dt
+        return A
+
+    def f_u(self, x, u, i):
+        """:585-603: J^-1 skew(m rho) R^T dt in the velocity rows."""
+        q, w = x
+        bt = self.Jinv @ lie.skew(self.m * self._rho()) @ lie.quat_to_rot(q).T
+        return np.vstack((np.zeros((3, 3)), bt)) * self.dt
+
+
 class SE3Dynamics:
     """traopt_dynamics.py:629-898."""
     state_size = 12

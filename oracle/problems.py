@@ -22,7 +22,7 @@ def load_golden(name):
         return {k: z[k] for k in z.files}
 
 
-def build(kind, J, dt, Q, R, P, q_ref, xi_ref):
+def build(kind, J, dt, Q, R, P, q_ref, xi_ref, m=None, length=None):
     """Return (dynamics, cost, group, q_ref in the group's pose type)."""
     if kind == "se3":
         return (models.SE3Dynamics(J, dt), models.SE3TrackingQuadraticGaussNewtonCost(Q, R, P, q_ref, xi_ref),
@@ -33,6 +33,9 @@ def build(kind, J, dt, Q, R, P, q_ref, xi_ref):
     if kind == "drone":
         return (models.DroneDynamics(J, dt), models.SE3TrackingQuadraticGaussNewtonCost(Q, R, P, q_ref, xi_ref),
                 solvers.SE3Group, [np.asarray(T, dtype=float) for T in q_ref])
+    if kind == "pendulum":
+        return (models.Pendulum3dDynamics(J, m, length, dt), models.SO3TrackingQuadraticGaussNewtonCost(Q, R, P, q_ref, xi_ref),
+                solvers.SO3Group, [lie.rot_to_quat(np.asarray(Rm, dtype=float)) for Rm in q_ref])
     if kind == "so3":
         return (models.SO3Dynamics(J, dt), models.SO3TrackingQuadraticGaussNewtonCost(Q, R, P, q_ref, xi_ref),
                 solvers.SO3Group, [lie.rot_to_quat(np.asarray(Rm, dtype=float)) for Rm in q_ref])
@@ -45,8 +48,8 @@ def from_golden(g, horizon=None):
     if horizon is not None:
         q_ref, xi_ref = q_ref[:horizon + 1], xi_ref[:horizon + 1]
     dyn, cost, group, q_ref_g = build(kind, g["prob_J"], float(g["prob_dt"]), g["prob_Q"], g["prob_R"],
-                                      g["prob_P"], q_ref, xi_ref)
-    if kind == "so3":
+                                      g["prob_P"], q_ref, xi_ref, m=g.get("prob_m"), length=g.get("prob_length"))
+    if kind in ("so3", "pendulum"):
         x0 = models.so3_state(g["prob_x0_q"], g["prob_x0_xi"])
     else:
         x0 = [np.array(g["prob_x0_q"]), np.array(g["prob_x0_xi"])]
@@ -56,6 +59,6 @@ def from_golden(g, horizon=None):
 
 def poses_to_matrices(kind, xs):
     """xs (oracle states) -> (poses as (N+1,4,4)|(N+1,3,3), velocities (N+1,6|3))."""
-    if kind == "so3":
+    if kind in ("so3", "pendulum"):
         return np.stack([lie.quat_to_rot(x[0]) for x in xs]), np.stack([x[1] for x in xs])
     return np.stack([x[0] for x in xs]), np.stack([x[1] for x in xs])

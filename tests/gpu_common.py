@@ -6,7 +6,7 @@ from oracle import problems
 
 def inertia_parts(kind, J):
     J = np.asarray(J, dtype=float)
-    if kind == "so3":
+    if kind in ("so3", "pendulum"):
         return J, 1.0
     return J[:3, :3], float(J[4, 4])
 
@@ -21,9 +21,11 @@ def make_solver(g, method, B, horizon=None, device="cuda", **params):
     N = q_ref.shape[0] - 1
     s = BatchSolver(kind, method, N, B, device=device)
     Ib, mass = inertia_parts(kind, g["prob_J"])
+    if kind == "pendulum":
+        mass, params = float(g["prob_m"]), dict(params, length=float(g["prob_length"]))
     s.set_params(dt=float(g["prob_dt"]), Ib=Ib, mass=mass, Q=g["prob_Q"], R=g["prob_R"], P=g["prob_P"], **params)
-    s.set_reference(layout.pose_rows(kind == "so3", q_ref), xi_ref)
-    x0 = np.concatenate((layout.pose_rows(kind == "so3", g["prob_x0_q"]), np.asarray(g["prob_x0_xi"], dtype=float).reshape(-1)))
+    s.set_reference(layout.pose_rows(kind in ("so3", "pendulum"), q_ref), xi_ref)
+    x0 = np.concatenate((layout.pose_rows(kind in ("so3", "pendulum"), g["prob_x0_q"]), np.asarray(g["prob_x0_xi"], dtype=float).reshape(-1)))
     return s, x0, N
 
 
@@ -41,7 +43,7 @@ def oracle_state(kind, row):
     """device state row -> oracle state [pose, velocity]."""
     from oracle import lie
     row = np.asarray(row, dtype=float)
-    if kind == "so3":
+    if kind in ("so3", "pendulum"):
         return [row[:4] / np.linalg.norm(row[:4]), row[4:7].copy()]
     q = row[:4] / np.linalg.norm(row[:4])
     return [lie.se3_to_matrix(q, row[4:7]), row[7:13].copy()]
@@ -52,7 +54,7 @@ def oracle_rows(kind, xs):
     from oracle import lie
     out = []
     for x in xs:
-        if kind == "so3":
+        if kind in ("so3", "pendulum"):
             out.append(np.concatenate((x[0], x[1])))
         else:
             q, p = lie.se3_from_matrix(x[0])

@@ -39,12 +39,14 @@ CASES = [
     ("draft1_so3_n249", "ss", 50, 1, [0] * 50),
     ("draft1_drone_n500", "ms", 150, 1, None),
     ("draft1_drone_n500", "ss", None, 2, [2, 0, 0, 3, 5, 7, 8, 9, 9, 9, 10, 10, 11, 11, -1]),
+    ("pendulum_n80", "ms", 100, 0, None),
+    ("pendulum_n80", "ss", 100, 1, [0] * 100),
 ]
 
 
 def _poses(kind, xs):
     from trajectory_optimization_matrix_lie_groups_b200 import layout
-    if kind == "so3":
+    if kind in ("so3", "pendulum"):
         return layout.quat_to_rot(xs[:, :4]), xs[:, 4:]
     return layout.rows_to_se3(xs[:, :7]), xs[:, 7:]
 

@@ -25,6 +25,7 @@ def _rel(a, b):
 @pytest.mark.parametrize("name,method,horizon", [
     ("se3_n120", "ms", None), ("se3_n120", "ss", None), ("so3_n249", "ms", 40), ("so3_n249", "ss", 40),
     ("drone_n150", "ms", 40), ("drone_n150", "ss", 40), ("rigid_n120", "ms", 40),
+    ("pendulum_n80", "ms", 40), ("pendulum_n80", "ss", 40),
 ])
 def test_linearization_matches_oracle(name, method, horizon):
     g = problems.load_golden(name)
@@ -54,7 +55,8 @@ def test_linearization_matches_oracle(name, method, horizon):
         assert np.all(L_ux == 0.0)      # the device never stores l_ux: it is identically zero on this path
 
 
-@pytest.mark.parametrize("name,method", [("se3_n120", "ms"), ("se3_n120", "ss"), ("so3_n249", "ms"), ("drone_n150", "ms")])
+@pytest.mark.parametrize("name,method", [("se3_n120", "ms"), ("se3_n120", "ss"), ("so3_n249", "ms"), ("drone_n150", "ms"),
+                                         ("pendulum_n80", "ms"), ("pendulum_n80", "ss")])
 def test_backward_gains_match_oracle(name, method):
     """One backward sweep from the initial trajectory: k, K against the oracle's LU-based solve."""
     horizon = 40
@@ -72,7 +74,7 @@ def test_backward_gains_match_oracle(name, method):
         us0 = np.zeros((N, dyn.action_size))
         if method == "ms":
             r = solvers.ilqr_ms(dyn, cost, group, N, q_ref, xi_ref, x0o, us0, n_iterations=1, tol_grad_norm=1e-30,
-                                n_alphas=13 if kind == "so3" else 20)
+                                n_alphas=13 if kind in ("so3", "pendulum") else 20)
         else:
             r = solvers.ilqr_ss(dyn, cost, group, N, x0o, us0, n_iterations=1, tol_grad_norm=1e-30)
         assert _rel(k_gpu[b], r.k) < 1e-9
@@ -80,7 +82,7 @@ def test_backward_gains_match_oracle(name, method):
         assert float(mu_gpu[b]) == r.mu_hist[0]
 
 
-@pytest.mark.parametrize("name", ["se3_n120", "drone_n150", "so3_n249", "rigid_n120"])
+@pytest.mark.parametrize("name", ["se3_n120", "drone_n150", "so3_n249", "rigid_n120", "pendulum_n80"])
 def test_dropin_class_callbacks_match_oracle(name):
     """The mirror classes' f / f_x / f_u / l / l_x / l_xx / _err are the CUDA library's numbers."""
     from trajectory_optimization_matrix_lie_groups_b200.traoptlibrary import traopt_cost, traopt_dynamics
@@ -89,8 +91,9 @@ def test_dropin_class_callbacks_match_oracle(name):
     kind = str(g["kind"])
     dyn_o, cost_o, group, q_ref_o, xi_ref, x0_o, N = problems.from_golden(g)
     J, dt, Q, R, P = g["prob_J"], float(g["prob_dt"]), g["prob_Q"], g["prob_R"], g["prob_P"]
-    if kind == "so3":
-        dyn = traopt_dynamics.SO3Dynamics(J, dt)
+    if kind in ("so3", "pendulum"):
+        dyn = (traopt_dynamics.SO3Dynamics(J, dt) if kind == "so3" else
+               traopt_dynamics.Pendulum3dDyanmics(J, float(g["prob_m"]), float(g["prob_length"]), dt))
         q_ref = [SO3(q) for q in q_ref_o]
         cost = traopt_cost.SO3TrackingQuadraticGaussNewtonCost(Q, R, P, q_ref, [SO3Tangent(w) for w in xi_ref])
     elif kind == "drone":
@@ -110,11 +113,11 @@ def test_dropin_class_callbacks_match_oracle(name):
         row = gc.oracle_rows(kind, [[q_ref_o[i], np.asarray(xi_ref[i], dtype=float)]])[0]
         row = gc.perturbed_x0(row, 2, seed=i, scale=0.05)[1]
         xo = gc.oracle_state(kind, row)
-        x = [SO3(xo[0]), SO3Tangent(xo[1])] if kind == "so3" else [xo[0], xo[1]]
+        x = [SO3(xo[0]), SO3Tangent(xo[1])] if kind in ("so3", "pendulum") else [xo[0], xo[1]]
         u = rng.standard_normal(m)
         fo = dyn_o.f(xo, u, i)
         fg = dyn.f(x, u, i)
-        if kind == "so3":
+        if kind in ("so3", "pendulum"):
             assert gc.quat_rows_close(np.concatenate((fg[0].coeffs(), fg[1].coeffs())), np.concatenate((fo[0], fo[1])), 7) < 1e-13
         else:
             assert np.max(np.abs(fg[0] - fo[0])) < 1e-13 and np.max(np.abs(fg[1] - fo[1])) < 1e-13

@@ -30,8 +30,8 @@ def _oracle(g, kind, method, horizon, x0_row, us0, n_iter, **kw):
         warnings.simplefilter("ignore")
         if method == "ms":
             return solvers.ilqr_ms(dyn, cost, group, N, q_ref, xi_ref, x0, us0, n_iterations=n_iter,
-                                   n_alphas=13 if kind == "so3" else 20,
-                                   defect_kappa=1e-14 if kind == "so3" else 1e-12, **kw)
+                                   n_alphas=13 if kind in ("so3", "pendulum") else 20,
+                                   defect_kappa=1e-14 if kind in ("so3", "pendulum") else 1e-12, **kw)
         return solvers.ilqr_ss(dyn, cost, group, N, x0, us0, n_iterations=n_iter, **kw)
 
 
@@ -82,6 +82,11 @@ def _compare(kind, out, hist, b, r, check_alpha=True):
     ("drone_n150", "ms", 30, 6, {}),
     ("drone_n150", "ss", 30, 6, {}),
     ("drone_n150", "ms", 30, 8, {"line_search": True}),
+    ("pendulum_n80", "ms", 30, 6, {}),
+    ("pendulum_n80", "ss", 30, 6, {}),
+    ("pendulum_n80", "ss", 30, 6, {"rollout": "linear"}),
+    ("pendulum_n80", "ms", 30, 6, {"rollout": "linear"}),
+    ("pendulum_n80", "ms", 30, 8, {"line_search": True}),
     ("rigid_n120", "ms", 30, 6, {}),
     ("rigid_n120", "ss", 12, 6, {}),      # (free fall over 30 stages of 0.05 s runs into the give-up branch)
     ("rigid_n120", "ms", 30, 6, {"rollout": "linear"}),

@@ -16,7 +16,7 @@ def _run(name, mode, max_iter=200, horizon=None):
     dyn, cost, group, q_ref, xi_ref, x0, N = problems.from_golden(g, horizon)
     us0 = np.zeros((N, dyn.action_size))
     if mode == "ms":
-        so3 = kind == "so3"
+        so3 = kind in ("so3", "pendulum")
         r = solvers.ilqr_ms(dyn, cost, group, N, q_ref, xi_ref, x0, us0, n_iterations=max_iter,
                             tol_grad_norm=1e-12, n_alphas=13 if so3 else 20,
                             defect_kappa=1e-14 if so3 else 1e-12, append_final_grad=so3)
@@ -147,3 +147,15 @@ def test_se3_ss_n955_line_search_decisions():
     g, kind, r = _run("se3_n955_r1e-5", "ss", max_iter=32)
     assert r.alpha_hist == [0] * 28 + [2, 8, 1, 11]
     _check_hist(r, g, "ss")
+
+
+def test_pendulum_n80_both_methods():
+    """Pendulum3dDyanmics (state-dependent f_u, gravity torque): the reference's swing-up result file."""
+    g, kind, r = _run("pendulum_n80", "ms", max_iter=100)
+    assert r.iterations == 19 and r.status == solvers.STATUS_CONVERGED
+    _check_hist(r, g, "ms")
+    _check_final(r, g, kind, "ms", 1e-10, 1e-12)
+    g, kind, r = _run("pendulum_n80", "ss", max_iter=100)
+    assert r.iterations == 100 and r.alpha_hist == [0] * 100
+    _check_hist(r, g, "ss")
+    _check_final(r, g, kind, "ss", 1e-10, 1e-12)

@@ -9,7 +9,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libtrajopt_b200.so")
 
-SO3, SE3, DRONE, RIGID = 0, 1, 2, 3
+SO3, SE3, DRONE, RIGID, PEND = 0, 1, 2, 3, 4
 SS, MS, AL_MS = 0, 1, 2
 STATUS_CONVERGED, STATUS_MAX_ITER, STATUS_NO_DESCENT, STATUS_RUNNING = 0, 1, 2, 3
 FLAG_REG_EXCEEDED, FLAG_NONFINITE = 16, 32
@@ -53,6 +53,7 @@ class Params(C.Structure):
         ("al_mu_scale", C.c_double),
         ("al_mu_max", C.c_double),
         ("tol_constr", C.c_double),
+        ("length", C.c_double),
     ]
 
 

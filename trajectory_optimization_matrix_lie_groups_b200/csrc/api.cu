@@ -152,7 +152,7 @@ static bool use_one_warp_sweep() {
 template <int KIND, bool MS>
 int run_backward(trajopt_handle* h, cudaStream_t s, int it) {
     PhaseTimer t(h, s, PH_BWD);
-    if constexpr (KIND != TRAJOPT_SO3) {
+    if constexpr (!on_so3(KIND)) {
         if (!use_one_warp_sweep()) {
             constexpr size_t smem3 = B3Smem<KIND>::BYTES;
             CUDA_OK(cudaFuncSetAttribute(k_backward3<KIND, MS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
@@ -355,7 +355,8 @@ int debug_stage_impl(trajopt_handle* h, int i, int terminal, int n, const double
     ((h)->kind == TRAJOPT_SO3   ? fn<TRAJOPT_SO3>(__VA_ARGS__)                \
      : (h)->kind == TRAJOPT_SE3 ? fn<TRAJOPT_SE3>(__VA_ARGS__)                \
      : (h)->kind == TRAJOPT_DRONE ? fn<TRAJOPT_DRONE>(__VA_ARGS__)            \
-                                  : fn<TRAJOPT_RIGID>(__VA_ARGS__))
+     : (h)->kind == TRAJOPT_RIGID ? fn<TRAJOPT_RIGID>(__VA_ARGS__)            \
+                                  : fn<TRAJOPT_PEND>(__VA_ARGS__))
 
 int ensure_hist(trajopt_handle* h) {
     const int cap = h->prm.max_iters;
@@ -401,10 +402,10 @@ int64_t trajopt_launch_count(int reset) {
 int trajopt_create(int kind, int method, int N, int B, int device, trajopt_handle** out) {
     if (!out) return fail(TRAJOPT_E_INVALID, "trajopt_create: out is NULL");
     *out = nullptr;
-    if (kind < TRAJOPT_SO3 || kind > TRAJOPT_RIGID) return fail(TRAJOPT_E_INVALID, "trajopt_create: unknown problem kind");
+    if (kind < TRAJOPT_SO3 || kind > TRAJOPT_PEND) return fail(TRAJOPT_E_INVALID, "trajopt_create: unknown problem kind");
     if (method < TRAJOPT_SS || method > TRAJOPT_AL_MS) return fail(TRAJOPT_E_INVALID, "trajopt_create: unknown method");
     if (N < 1 || N > 65534 || B < 1) return fail(TRAJOPT_E_INVALID, "trajopt_create: need 1 <= N <= 65534 and B >= 1");
-    if (method == TRAJOPT_AL_MS && kind == TRAJOPT_SO3)
+    if (method == TRAJOPT_AL_MS && on_so3(kind))
         return fail(TRAJOPT_E_INVALID, "trajopt_create: the augmented-Lagrangian controller exists for SE3 problems only");
     int ndev = 0;
     CUDA_OK(cudaGetDeviceCount(&ndev));
@@ -415,6 +416,7 @@ int trajopt_create(int kind, int method, int N, int B, int device, trajopt_handl
     h->kind = kind; h->method = method; h->N = N; h->B = B; h->device = device;
     h->Bp = (B + kBlock - 1) / kBlock * kBlock;
     if (kind == TRAJOPT_SO3) { h->NX = 6; h->NP = 3; h->NU = 3; h->NS = 7; h->LEN = LinRec<TRAJOPT_SO3>::LEN; h->REFROW = RefRow<TRAJOPT_SO3>::N; }
+    else if (kind == TRAJOPT_PEND) { h->NX = 6; h->NP = 3; h->NU = 3; h->NS = 7; h->LEN = LinRec<TRAJOPT_PEND>::LEN; h->REFROW = RefRow<TRAJOPT_PEND>::N; }
     else if (kind == TRAJOPT_SE3) { h->NX = 12; h->NP = 6; h->NU = 6; h->NS = 13; h->LEN = LinRec<TRAJOPT_SE3>::LEN; h->REFROW = RefRow<TRAJOPT_SE3>::N; }
     else if (kind == TRAJOPT_DRONE) { h->NX = 12; h->NP = 6; h->NU = 4; h->NS = 13; h->LEN = LinRec<TRAJOPT_DRONE>::LEN; h->REFROW = RefRow<TRAJOPT_DRONE>::N; }
     else { h->NX = 12; h->NP = 6; h->NU = 6; h->NS = 13; h->LEN = LinRec<TRAJOPT_RIGID>::LEN; h->REFROW = RefRow<TRAJOPT_RIGID>::N; }
@@ -429,7 +431,7 @@ int trajopt_create(int kind, int method, int N, int B, int device, trajopt_handl
     A_(w.lin, Np1 * h->LEN * Bp);
     A_(w.Lc, Np1 * Bp); A_(w.Dsq, (size_t)N * Bp);
     if (method != TRAJOPT_SS) {
-        const int gl = (kind == TRAJOPT_SO3) ? GPre<TRAJOPT_SO3>::LEN : GPre<TRAJOPT_SE3>::LEN;
+        const int gl = on_so3(kind) ? GPre<TRAJOPT_SO3>::LEN : GPre<TRAJOPT_SE3>::LEN;
         A_(w.Gpre, (size_t)N * gl * Bp);
     }
     A_(w.kff, (size_t)N * h->NU * Bp); A_(w.Kfb, (size_t)N * h->NU * h->NX * Bp);
@@ -482,7 +484,7 @@ int trajopt_set_params(trajopt_handle* h, const trajopt_params* p) {
     q.kind = h->kind; q.N = h->N; q.B = h->B; q.Bp = h->Bp; q.method = h->method;
     q.rollout_linear = p->rollout_linear ? 1 : 0;
     q.line_search = (h->method != TRAJOPT_SS && p->line_search) ? 1 : 0;
-    q.n_alphas = p->n_alphas > 0 ? p->n_alphas : ((h->method == TRAJOPT_SS || h->kind == TRAJOPT_SO3) ? 13 : 20);
+    q.n_alphas = p->n_alphas > 0 ? p->n_alphas : ((h->method == TRAJOPT_SS || on_so3(h->kind)) ? 13 : 20);
     if (q.n_alphas > 64) return fail(TRAJOPT_E_INVALID, "trajopt_set_params: n_alphas > 64");
     q.max_iters = p->max_iters;
     q.has_constraints = (h->method == TRAJOPT_AL_MS) ? 1 : 0;
@@ -491,6 +493,8 @@ int trajopt_set_params(trajopt_handle* h, const trajopt_params* p) {
     inv3(q.Ib, q.Ibinv);
     q.mass = p->mass;
     q.grav = p->gravity;
+    q.length = p->length;
+    if (h->kind == TRAJOPT_PEND && !(p->length > 0.0)) return fail(TRAJOPT_E_INVALID, "trajopt_set_params: the pendulum needs length > 0");
     memset(q.W1, 0, sizeof(q.W1)); memset(q.W2, 0, sizeof(q.W2));
     memset(q.P1, 0, sizeof(q.P1)); memset(q.P2, 0, sizeof(q.P2));
     memset(q.R, 0, sizeof(q.R)); memset(q.Bv, 0, sizeof(q.Bv));
@@ -526,8 +530,8 @@ int trajopt_set_params(trajopt_handle* h, const trajopt_params* p) {
     q.mu_max = p->max_reg;
     q.delta0 = 2.0;
     q.defect_mu0 = 10.0; q.defect_rho = 0.5; q.defect_gamma = 0.05;   // :2406-2410
-    q.defect_kappa = p->defect_kappa > 0.0 ? p->defect_kappa : (h->kind == TRAJOPT_SO3 ? 1e-14 : 1e-12);
-    q.so3_terminal_quirk = (h->kind == TRAJOPT_SO3) ? 1 : 0;
+    q.defect_kappa = p->defect_kappa > 0.0 ? p->defect_kappa : (on_so3(h->kind) ? 1e-14 : 1e-12);
+    q.so3_terminal_quirk = on_so3(h->kind) ? 1 : 0;
     int rc = ensure_hist(h);
     if (rc) return rc;
     h->have_params = true;
@@ -542,7 +546,7 @@ int trajopt_set_reference(trajopt_handle* h, const double* h_q_ref, const double
     std::vector<double> rows((size_t)(h->N + 1) * rr);
     for (int i = 0; i <= h->N; ++i) {
         double* r = rows.data() + (size_t)i * rr;
-        if (h->kind == TRAJOPT_SO3) {
+        if (on_so3(h->kind)) {
             const double* q = h_q_ref + (size_t)i * 4;
             const double nq = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
             if (!(nq > 0.0)) return fail(TRAJOPT_E_INVALID, "trajopt_set_reference: zero quaternion");

@@ -13,8 +13,8 @@
 //   Vxs  V_x(i+1), then Q_x, then V_x(i)                        NX
 // The dynamics Jacobian A = f_x is never assembled: its nonzero 3x3 blocks are read from the
 // linearisation record when a column block needs them,
-//   SE3/drone   [ a   0   c    0     ]        SO3   [ a  c ]
-//               [ b   a   e    c     ]              [ 0  h ]
+//   SE3/drone   [ a   0   c    0     ]        SO3   [ a  c ]      pendulum  [ a  c ]
+//               [ b   a   e    c     ]              [ 0  h ]                [ l  h ]
 //               [ 0   0   h11  h12   ]
 //               [(s^) 0   vdt^ I-vdt^]
 // Algebra per stage (equal to :3052-3060 and :2993-3004 up to rounding):
@@ -42,14 +42,14 @@ enum { BK_ZERO = 0, BK_DENSE = 1, BK_SKEW = 2, BK_IMSKEW = 3 };
 
 // kind and record offset of the 3x3 block (rb, cb) of A
 template <int KIND> __host__ __device__ constexpr int blk_kind(int rb, int cb) {
-    if (KIND == TRAJOPT_SO3) return (rb == 1 && cb == 0) ? BK_ZERO : BK_DENSE;
+    if (on_so3(KIND)) return (rb == 1 && cb == 0) ? (KIND == TRAJOPT_PEND ? BK_DENSE : BK_ZERO) : BK_DENSE;
     if (cb == 0) return (rb == 0 || rb == 1) ? BK_DENSE : ((rb == 3 && has_gravity(KIND)) ? BK_SKEW : BK_ZERO);
     if (cb == 1) return rb == 1 ? BK_DENSE : BK_ZERO;
     if (cb == 2) return rb == 3 ? BK_SKEW : BK_DENSE;
     return rb == 0 ? BK_ZERO : (rb == 3 ? BK_IMSKEW : BK_DENSE);
 }
 template <int KIND> __host__ __device__ constexpr int blk_off(int rb, int cb) {
-    if (KIND == TRAJOPT_SO3) return cb == 0 ? 0 : (rb == 0 ? 9 : 18);
+    if (on_so3(KIND)) return cb == 0 ? (rb == 0 ? 0 : 27) : (rb == 0 ? 9 : 18);
     if (cb == 0) return rb == 0 ? 0 : (rb == 1 ? 9 : 57);
     if (cb == 1) return 0;
     if (cb == 2) return rb == 0 ? 18 : (rb == 1 ? 27 : (rb == 2 ? 36 : 54));
@@ -159,6 +159,7 @@ __global__ void __launch_bounds__(kBlock) k_backward(const Params prm, Work w, i
 
     for (int i = N - 1; i >= 0; --i) {
         const double* __restrict__ rec = lin + lsoa(i, 0, F, N + 1, b);
+        const BvStage<KIND> Bv(prm, rec, kRecStride);   // velocity rows of f_u: constant, or per stage (pendulum)
         if (i > 0) {   // pull the next record towards L2 while this stage computes
             const char* nxt = (const char*)(lin + lsoa(i - 1, 0, F, N + 1, b - lane));
 #pragma unroll
@@ -198,7 +199,7 @@ __global__ void __launch_bounds__(kBlock) k_backward(const Params prm, Work w, i
             double s = lu[a];
 #pragma unroll
             for (int r = 0; r < NV; ++r)
-                if (bv_nz<KIND>(r, a)) s = fma(prm.Bv[r * NU + a], v[NP + r], s);
+                if (bv_nz<KIND>(r, a)) s = fma(Bv.get(r, a), v[NP + r], s);
             Qu[a] = s;
         }
         if constexpr (MS) {
@@ -215,7 +216,7 @@ __global__ void __launch_bounds__(kBlock) k_backward(const Params prm, Work w, i
                 double s = lu[a];
 #pragma unroll
                 for (int r = 0; r < NV; ++r)
-                    if (bv_nz<KIND>(r, a)) s = fma(prm.Bv[r * NU + a], pad[NP + r], s);
+                    if (bv_nz<KIND>(r, a)) s = fma(Bv.get(r, a), pad[NP + r], s);
                 g2 += s * s;
             }
             gsum += sqrt(g2);
@@ -274,7 +275,7 @@ __global__ void __launch_bounds__(kBlock) k_backward(const Params prm, Work w, i
                     double s = 0.0;
 #pragma unroll
                     for (int k = 0; k < NV; ++k)
-                        if (bv_nz<KIND>(k, a)) s = fma(vr[k], prm.Bv[k * NU + a], s);
+                        if (bv_nz<KIND>(k, a)) s = fma(vr[k], Bv.get(k, a), s);
                     T[r * NU + a] = s;
                 }
             }
@@ -286,7 +287,7 @@ __global__ void __launch_bounds__(kBlock) k_backward(const Params prm, Work w, i
                     if (a == c) s += rec[(size_t)(LR::LUU_OFF + a) * kRecStride];
 #pragma unroll
                     for (int r = 0; r < NV; ++r)
-                        if (bv_nz<KIND>(r, a)) s = fma(prm.Bv[r * NU + a], T[r * NU + c], s);
+                        if (bv_nz<KIND>(r, a)) s = fma(Bv.get(r, a), T[r * NU + c], s);
                     Quu0[a * NU + c] = s;
                 }
         }
@@ -301,7 +302,7 @@ __global__ void __launch_bounds__(kBlock) k_backward(const Params prm, Work w, i
             // (compile-time indices throughout: a rolled loop here would push Lc into local memory)
             sfor<0, NU>([&](auto cc) {
                 constexpr int c = decltype(cc)::value;
-                double dg = fma(mu_used, prm.BtB[c * NU + c], Quu0[c * NU + c]);
+                double dg = fma(mu_used, Bv.btb(prm, c, c), Quu0[c * NU + c]);
                 sfor<0, c>([&](auto kc) {
                     constexpr int k = decltype(kc)::value;
                     dg = fma(-Lc[c * NU + k], Lc[c * NU + k], dg);
@@ -311,7 +312,7 @@ __global__ void __launch_bounds__(kBlock) k_backward(const Params prm, Work w, i
                 Lc[c * NU + c] = inv;
                 sfor<c + 1, NU>([&](auto rc) {
                     constexpr int r = decltype(rc)::value;
-                    double sacc = fma(mu_used, prm.BtB[c * NU + r], Quu0[c * NU + r]);
+                    double sacc = fma(mu_used, Bv.btb(prm, c, r), Quu0[c * NU + r]);
                     sfor<0, c>([&](auto kc) {
                         constexpr int k = decltype(kc)::value;
                         sacc = fma(-Lc[r * NU + k], Lc[c * NU + k], sacc);
@@ -396,7 +397,7 @@ __global__ void __launch_bounds__(kBlock) k_backward(const Params prm, Work w, i
 #pragma unroll
                                 for (int ii = 0; ii < 3; ++ii)
                                     if (bv_nz<KIND>(KB * 3 + ii - NP, a)) {
-                                        const double bm = mu_used * prm.Bv[(KB * 3 + ii - NP) * NU + a];
+                                        const double bm = mu_used * Bv.get(KB * 3 + ii - NP, a);
 #pragma unroll
                                         for (int j = 0; j < 3; ++j)
                                             if (blk_nz(kind, ii, j)) Qux[a][j] = fma(bm, m[3 * ii + j], Qux[a][j]);
@@ -412,7 +413,7 @@ __global__ void __launch_bounds__(kBlock) k_backward(const Params prm, Work w, i
                 for (int r = 0; r < NV; ++r)
                     if (bv_nz<KIND>(r, a)) {
 #pragma unroll
-                        for (int j = 0; j < 3; ++j) Qux[a][j] = fma(prm.Bv[r * NU + a], X[NP + r][j], Qux[a][j]);
+                        for (int j = 0; j < 3; ++j) Qux[a][j] = fma(Bv.get(r, a), X[NP + r][j], Qux[a][j]);
                     }
             // Y = L^-1 Q_ux (in place), K = -L^-T Y
 #pragma unroll

@@ -363,7 +363,7 @@ TO_DEV void b3_store_block(double* __restrict__ Vs, const double (&acc)[3][3]) {
 
 template <int KIND, bool MS>
 __global__ void __launch_bounds__(kB3Threads, 4) k_backward3(const Params prm, Work w, int it) {
-    static_assert(KIND != TRAJOPT_SO3, "the 3-warp sweep is for the 12-dimensional families");
+    static_assert(!on_so3(KIND), "the 3-warp sweep is for the 12-dimensional families");
     using D = Dims<KIND>;
     using LR = LinRec<KIND>;
     using SM = B3Smem<KIND>;

@@ -19,6 +19,10 @@ template <> struct Dims<TRAJOPT_SO3>   { static constexpr int NX = 6,  NP = 3, N
 template <> struct Dims<TRAJOPT_SE3>   { static constexpr int NX = 12, NP = 6, NU = 6, NS = 13; };
 template <> struct Dims<TRAJOPT_DRONE> { static constexpr int NX = 12, NP = 6, NU = 4, NS = 13; };
 template <> struct Dims<TRAJOPT_RIGID> { static constexpr int NX = 12, NP = 6, NU = 6, NS = 13; };
+template <> struct Dims<TRAJOPT_PEND>  { static constexpr int NX = 6,  NP = 3, NU = 3, NS = 7;  };
+
+// attitude-only families: pose = unit quaternion, 6-dimensional tangent state
+__host__ __device__ constexpr bool on_so3(int kind) { return kind == TRAJOPT_SO3 || kind == TRAJOPT_PEND; }
 
 // gravity acts on the body (quadrotor, rigid body): f gets m g R^T(-e3), f_x a lower-left skew block
 __host__ __device__ constexpr bool has_gravity(int kind) { return kind == TRAJOPT_DRONE || kind == TRAJOPT_RIGID; }
@@ -26,7 +30,7 @@ __host__ __device__ constexpr bool has_gravity(int kind) { return kind == TRAJOP
 // Doubles per reference-trajectory row (shared by the whole batch, read with uniform loads):
 //   SE3/drone: q_ref quat(4) p_ref(3) xi_ref(6) R_ref(9) [p_ref]x R_ref (9)            = 31
 //   SO3      : q_ref quat(4) w_ref(3) R_ref(9)                                          = 16
-template <int KIND> struct RefRow { static constexpr int N = (KIND == TRAJOPT_SO3) ? 16 : 31; };
+template <int KIND> struct RefRow { static constexpr int N = on_so3(KIND) ? 16 : 31; };
 
 // Per-stage linearisation record written by the stage-parallel kernel and read by the
 // backward sweep.  Layout in HBM is group-major: [group of 32 problems][stage][field][32], so the
@@ -34,11 +38,12 @@ template <int KIND> struct RefRow { static constexpr int N = (KIND == TRAJOPT_SO
 // first STAGE_LEN fields (what every warp of the backward CTA needs repeatedly) are brought into
 // shared memory by a single TMA bulk copy per stage.  Field offsets:
 //   SE3/drone:  a(9) b(9) c(9) e(9) h11(9) h12(9) vdt(3) [s(3) drone] | d(12) lu(NU) | luu_add(NU, AL) lx(12) lxx(21)
-//   SO3      :  a(9) c(9) h(9)                                        | d(6)  lu(3)  | luu_add(3)      lx(6)  lxx(6)
+//   SO3      :  a(9) c(9) h(9) [pendulum: l(9) = lower-left block, bv(9)]  | d(6)  lu(3)  | luu_add(3)      lx(6)  lxx(6)
 template <int KIND> struct LinRec {
     using D = Dims<KIND>;
     static constexpr int A_OFF = 0;
-    static constexpr int A_LEN = (KIND == TRAJOPT_SO3) ? 27 : (has_gravity(KIND) ? 60 : 57);
+    static constexpr int A_LEN = (KIND == TRAJOPT_SO3) ? 27 : (KIND == TRAJOPT_PEND) ? 45 : (has_gravity(KIND) ? 60 : 57);
+    static constexpr int BV_OFF = 36;                   // pendulum only: per-stage velocity rows of f_u (3 x 3) inside the A part
     static constexpr int D_OFF = A_OFF + A_LEN;
     static constexpr int LU_OFF = D_OFF + D::NX;
     static constexpr int STAGE_LEN = LU_OFF + D::NU;    // prefix staged in shared memory by the backward sweep
@@ -61,7 +66,7 @@ struct Params {
     int max_iters;
     int has_constraints;         // AL: box bounds on u
     double dt;
-    double Ib[9], Ibinv[9], mass, grav;
+    double Ib[9], Ibinv[9], mass, grav, length;
     double W1[36], W2[36];       // stage weights: pose block / velocity block (NP x NP, row-major, leading dim NP)
     double P1[36], P2[36];       // terminal weights
     double R[36];                // NU x NU

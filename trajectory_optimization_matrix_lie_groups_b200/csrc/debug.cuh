@@ -126,7 +126,7 @@ __global__ void k_debug_stage(const Params prm, const double* __restrict__ ref, 
         for (int j = 0; j < NS; ++j) row[j] = xin[(size_t)r * NS + j];
         quat_normalize(row);
         for (int j = 0; j < 4; ++j) x.q[j] = row[j];
-        if constexpr (KIND != TRAJOPT_SO3) {
+        if constexpr (!on_so3(KIND)) {
             for (int j = 0; j < 3; ++j) x.p[j] = row[4 + j];
             for (int j = 0; j < 6; ++j) x.xi[j] = row[7 + j];
         } else {
@@ -140,7 +140,7 @@ __global__ void k_debug_stage(const Params prm, const double* __restrict__ ref, 
         dyn_step<KIND>(prm, x, u, xn);
         double* o = f_out + (size_t)r * NS;
         for (int j = 0; j < 4; ++j) o[j] = xn.q[j];
-        if constexpr (KIND != TRAJOPT_SO3) {
+        if constexpr (!on_so3(KIND)) {
             for (int j = 0; j < 3; ++j) o[4 + j] = xn.p[j];
             for (int j = 0; j < 6; ++j) o[7 + j] = xn.xi[j];
         } else {
@@ -149,7 +149,7 @@ __global__ void k_debug_stage(const Params prm, const double* __restrict__ ref, 
     }
     if (Fx) {
         double rec[LR::A_LEN];
-        dyn_jacobian<KIND>(prm, x, rec);
+        dyn_jacobian<KIND>(prm, x, u, rec);
         double* o = Fx + (size_t)r * NX * NX;
         for (int j = 0; j < NX * NX; ++j) o[j] = 0.0;
         sfor<0, NB>([&](auto rbc) {
@@ -165,9 +165,12 @@ __global__ void k_debug_stage(const Params prm, const double* __restrict__ ref, 
         });
     }
     if (Fu) {
+        double rec[LR::A_LEN];
+        if constexpr (KIND == TRAJOPT_PEND) dyn_jacobian<KIND>(prm, x, u, rec);    // f_u depends on the attitude
+        const BvStage<KIND> Bv(prm, rec, 1);
         double* o = Fu + (size_t)r * NX * NU;
         for (int a = 0; a < NX; ++a)
-            for (int c = 0; c < NU; ++c) o[a * NU + c] = (a >= NP && bv_nz<KIND>(a - NP, c)) ? prm.Bv[(a - NP) * NU + c] : 0.0;
+            for (int c = 0; c < NU; ++c) o[a * NU + c] = (a >= NP && bv_nz<KIND>(a - NP, c)) ? Bv.get(a - NP, c) : 0.0;
     }
     if (l_out || lx_out || lxx_out) {
         double lx[NX], lxx[LR::LXX_LEN];

@@ -57,7 +57,7 @@ constexpr int kBlock = 32;
 // besides x(i), u(i): the pose G_i = q(i+1) Exp(d_q) f(x_i,u_i).q^-1 and f(x_i,u_i).xi (traopt_controller.py:2697-2718).
 // Both are independent of the rollout's recursion, so the stage-parallel linearisation forms them.
 template <int KIND> struct GPre {
-    static constexpr int NPOSE = (KIND == TRAJOPT_SO3) ? 4 : 7;
+    static constexpr int NPOSE = (on_so3(KIND)) ? 4 : 7;
     static constexpr int LEN = NPOSE + (Dims<KIND>::NX - Dims<KIND>::NP);
 };
 
@@ -75,27 +75,32 @@ __host__ __device__ constexpr double skew_sign(int i, int j) {
     return (i == j) ? 0.0 : (((j - i + 3) % 3 == 1) ? -1.0 : 1.0);
 }
 
-template <> struct AMat<TRAJOPT_SO3> {
-    double a[9], c[9], h[9];
-    static __host__ __device__ constexpr bool nz(int r, int cc) { return !(r >= 3 && cc < 3); }
+// attitude families: [ a  c ; l  h ], l = 0 except for the pendulum
+template <int KIND> struct AMatSO3 {
+    double a[9], c[9], h[9], l[9];
+    static __host__ __device__ constexpr bool nz(int r, int cc) { return KIND == TRAJOPT_PEND || !(r >= 3 && cc < 3); }
     TO_DEV double get(int r, int cc) const {
         const int i = r % 3, j = cc % 3;
         if (r < 3 && cc < 3) return a[3 * i + j];
         if (r < 3) return c[3 * i + j];
+        if (cc < 3) return l[3 * i + j];
         return h[3 * i + j];
     }
     TO_DEV void load(const double* __restrict__ lin, int stage, int Np1, int b) {
-        constexpr int F = LinRec<TRAJOPT_SO3>::LEN;
+        constexpr int F = LinRec<KIND>::LEN;
 #pragma unroll
         for (int i = 0; i < 9; ++i) {
             a[i] = lin[lsoa(stage, i, F, Np1, b)];
             c[i] = lin[lsoa(stage, 9 + i, F, Np1, b)];
             h[i] = lin[lsoa(stage, 18 + i, F, Np1, b)];
+            l[i] = (KIND == TRAJOPT_PEND) ? lin[lsoa(stage, 27 + i, F, Np1, b)] : 0.0;
         }
     }
 };
+template <> struct AMat<TRAJOPT_SO3> : AMatSO3<TRAJOPT_SO3> {};
+template <> struct AMat<TRAJOPT_PEND> : AMatSO3<TRAJOPT_PEND> {};
 
-template <int KIND> struct AMat {   // SE3 and DRONE
+template <int KIND> struct AMat {   // SE3, drone, rigid body
     double a[9], b[9], c[9], e[9], h11[9], h12[9], vdt[3], s[3];
     static __host__ __device__ constexpr bool nz(int r, int cc) {
         const int br = r / 3, bc = cc / 3, i = r % 3, j = cc % 3;
@@ -139,10 +144,28 @@ template <int KIND> struct AMat {   // SE3 and DRONE
 
 // Velocity rows of f_u: Bv = Jinv Pu dt  (NV x NU), compile-time sparsity
 template <int KIND> __host__ __device__ constexpr bool bv_nz(int r, int c) {
-    if (KIND == TRAJOPT_SO3) return true;
+    if (on_so3(KIND)) return true;
     if (KIND == TRAJOPT_SE3 || KIND == TRAJOPT_RIGID) return (r < 3 && c < 3) || (r >= 3 && r == c);
     return (r < 3 && c < 3) || (r == 5 && c == 3);   // drone: torques + body-z thrust
 }
+
+// Velocity rows of f_u for one stage.  Constant for the rigid-body families (Params::Bv); the pendulum's
+// depend on the attitude (J^-1 skew(m rho) R^T dt, traopt_dynamics.py:590-603) and come from the record.
+template <int KIND> struct BvStage {
+    const Params& prm;
+    TO_DEV BvStage(const Params& p, const double*, int) : prm(p) {}
+    TO_DEV double get(int r, int a) const { return prm.Bv[r * Dims<KIND>::NU + a]; }
+    TO_DEV double btb(const Params&, int a, int c) const { return prm.BtB[a * Dims<KIND>::NU + c]; }   // (Bv^T Bv)[a][c]
+};
+template <> struct BvStage<TRAJOPT_PEND> {
+    double v[9];
+    TO_DEV BvStage(const Params&, const double* __restrict__ rec, int stride) {
+#pragma unroll
+        for (int t = 0; t < 9; ++t) v[t] = rec[(size_t)(LinRec<TRAJOPT_PEND>::BV_OFF + t) * stride];
+    }
+    TO_DEV double get(int r, int a) const { return v[r * 3 + a]; }
+    TO_DEV double btb(const Params&, int a, int c) const { return fma(v[a], v[c], fma(v[3 + a], v[3 + c], v[6 + a] * v[6 + c])); }
+};
 
 __host__ __device__ constexpr int tri_idx(int n, int r, int c) {   // packed upper triangle, r <= c
     return r * n - (r * (r - 1)) / 2 + (c - r);
@@ -224,7 +247,7 @@ __global__ void k_init_ms(const Params prm, Work w, bool only_running) {
     if (stage == 0) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) s.q[j] = w.x0[(size_t)j * prm.Bp + b];
-        if constexpr (KIND != TRAJOPT_SO3) {
+        if constexpr (!on_so3(KIND)) {
 #pragma unroll
             for (int j = 0; j < 3; ++j) s.p[j] = w.x0[(size_t)(4 + j) * prm.Bp + b];
 #pragma unroll
@@ -253,7 +276,7 @@ __global__ void __launch_bounds__(kBlock) k_init_ss(const Params prm, Work w) {
     State<KIND> x, xn;
 #pragma unroll
     for (int j = 0; j < 4; ++j) x.q[j] = w.x0[(size_t)j * prm.Bp + b];
-    if constexpr (KIND != TRAJOPT_SO3) {
+    if constexpr (!on_so3(KIND)) {
 #pragma unroll
         for (int j = 0; j < 3; ++j) x.p[j] = w.x0[(size_t)(4 + j) * prm.Bp + b];
 #pragma unroll
@@ -336,7 +359,7 @@ __global__ void __launch_bounds__(128) k_linearize(const Params prm, Work w) {
         }
         // dynamics Jacobian
         double rec[LR::A_LEN];
-        dyn_jacobian<KIND>(prm, x, rec);
+        dyn_jacobian<KIND>(prm, x, u, rec);
 #pragma unroll
         for (int j = 0; j < LR::A_LEN; ++j) out[lsoa(stage, LR::A_OFF + j, F, prm.N + 1, b)] = rec[j];
         // defect against the next shooting node
@@ -356,7 +379,7 @@ __global__ void __launch_bounds__(128) k_linearize(const Params prm, Work w) {
             {
                 constexpr int GL = GPre<KIND>::LEN, GP = GPre<KIND>::NPOSE;
                 double* gp = w.Gpre + soa(stage, 0, GL, Bp, b);
-                if constexpr (KIND == TRAJOPT_SO3) {
+                if constexpr (on_so3(KIND)) {
                     double qe[4], q1[4], q2[4];
                     so3_exp(d, qe);
                     quat_compose(xnext.q, qe, q1);

@@ -90,6 +90,7 @@ __global__ void __launch_bounds__(kBlock) k_forward(const Params prm, Work w, in
             // step = A dx + B du (+ alpha d), pose part retracts x(i+1)
             AMat<KIND> A;
             A.load(lin, i, N + 1, b);
+            const BvStage<KIND> Bv(prm, lin + lsoa(i, 0, F, N + 1, b), kRecStride);
             double st[NX];
 #pragma unroll
             for (int r = 0; r < NX; ++r) {
@@ -100,12 +101,12 @@ __global__ void __launch_bounds__(kBlock) k_forward(const Params prm, Work w, in
                 if (r >= NP) {
 #pragma unroll
                     for (int a = 0; a < NU; ++a)
-                        if (bv_nz<KIND>(r - NP, a)) s += prm.Bv[(r - NP) * NU + a] * du[a];
+                        if (bv_nz<KIND>(r - NP, a)) s += Bv.get(r - NP, a) * du[a];
                 }
                 if constexpr (MS) s += alpha * lin[lsoa(i, LR::D_OFF + r, F, N + 1, b)];
                 st[r] = s;
             }
-            if constexpr (KIND == TRAJOPT_SO3) {
+            if constexpr (on_so3(KIND)) {
                 double qe[4];
                 so3_exp(st, qe);
                 quat_compose(xnext.q, qe, xn1.q);
@@ -125,7 +126,7 @@ __global__ void __launch_bounds__(kBlock) k_forward(const Params prm, Work w, in
                 double d[NX];
 #pragma unroll
                 for (int j = 0; j < NX; ++j) d[j] = alpha * lin[lsoa(i, LR::D_OFF + j, F, N + 1, b)];
-                if constexpr (KIND == TRAJOPT_SO3) {
+                if constexpr (on_so3(KIND)) {
                     double qe[4], q1[4], q2[4];
                     so3_exp(d, qe);
                     quat_compose(xnext.q, qe, q1);
@@ -277,7 +278,7 @@ __global__ void __launch_bounds__(kBlock) k_forward_ms_full(const Params prm, Wo
         }
         State<KIND> fnew, xn1;
         dyn_step<KIND>(prm, xnew, unew, fnew);
-        if constexpr (KIND == TRAJOPT_SO3) {
+        if constexpr (on_so3(KIND)) {
             quat_compose(G, fnew.q, xn1.q);
         } else {
             se3_compose(G, G + 4, fnew.q, fnew.p, xn1.q, xn1.p);
@@ -417,6 +418,7 @@ __global__ void __launch_bounds__(kBlock) k_ms_expected(const Params prm, Work w
         // propagate
         AMat<KIND> A;
         A.load(lin, i, N + 1, b);
+        const BvStage<KIND> Bv(prm, lin + lsoa(i, 0, F, N + 1, b), kRecStride);
         double st[NX];
 #pragma unroll
         for (int r = 0; r < NX; ++r) {
@@ -427,12 +429,12 @@ __global__ void __launch_bounds__(kBlock) k_ms_expected(const Params prm, Work w
             if (r >= NP) {
 #pragma unroll
                 for (int a = 0; a < NU; ++a)
-                    if (bv_nz<KIND>(r - NP, a)) s += prm.Bv[(r - NP) * NU + a] * du[a];
+                    if (bv_nz<KIND>(r - NP, a)) s += Bv.get(r - NP, a) * du[a];
             }
             st[r] = s;
         }
         // pose part goes through Exp then Log (rminus of the retracted pose against the node)
-        if constexpr (KIND == TRAJOPT_SO3) {
+        if constexpr (on_so3(KIND)) {
             double qe[4];
             so3_exp(st, qe);
             so3_log(qe, dx);
@@ -647,9 +649,10 @@ __global__ void k_export_lin(const Params prm, Work w, double* Fx, double* Fu, d
                 Fx[(((size_t)b * N + i) * NX + r) * NX + c] = AMat<KIND>::nz(r, c) ? A.get(r, c) : 0.0;
     }
     if (Fu) {
+        const BvStage<KIND> Bv(prm, lin + lsoa(i, 0, F, N + 1, b), kRecStride);
         for (int r = 0; r < NX; ++r)
             for (int a = 0; a < NU; ++a)
-                Fu[(((size_t)b * N + i) * NX + r) * NU + a] = (r >= NP && bv_nz<KIND>(r - NP, a)) ? prm.Bv[(r - NP) * NU + a] : 0.0;
+                Fu[(((size_t)b * N + i) * NX + r) * NU + a] = (r >= NP && bv_nz<KIND>(r - NP, a)) ? Bv.get(r - NP, a) : 0.0;
     }
     if (dd)
         for (int c = 0; c < NX; ++c) dd[((size_t)b * N + i) * NX + c] = lin[lsoa(i, LR::D_OFF + c, F, N + 1, b)];

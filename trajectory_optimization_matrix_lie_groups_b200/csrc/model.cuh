@@ -32,7 +32,7 @@ TO_DEV void load_state(const double* __restrict__ X, int stage, int Bp, int b, S
     const double* base = X + soa(stage, 0, NS, Bp, b);
 #pragma unroll
     for (int j = 0; j < 4; ++j) s.q[j] = base[(size_t)j * Bp];
-    if constexpr (KIND != TRAJOPT_SO3) {
+    if constexpr (!on_so3(KIND)) {
 #pragma unroll
         for (int j = 0; j < 3; ++j) s.p[j] = base[(size_t)(4 + j) * Bp];
 #pragma unroll
@@ -48,7 +48,7 @@ TO_DEV void store_state(double* __restrict__ X, int stage, int Bp, int b, const 
     double* base = X + soa(stage, 0, NS, Bp, b);
 #pragma unroll
     for (int j = 0; j < 4; ++j) base[(size_t)j * Bp] = s.q[j];
-    if constexpr (KIND != TRAJOPT_SO3) {
+    if constexpr (!on_so3(KIND)) {
 #pragma unroll
         for (int j = 0; j < 3; ++j) base[(size_t)(4 + j) * Bp] = s.p[j];
 #pragma unroll
@@ -63,7 +63,7 @@ TO_DEV void load_ref_state(const double* __restrict__ ref, int stage, State<KIND
     const double* r = ref + (size_t)stage * RefRow<KIND>::N;
 #pragma unroll
     for (int j = 0; j < 4; ++j) s.q[j] = r[j];
-    if constexpr (KIND != TRAJOPT_SO3) {
+    if constexpr (!on_so3(KIND)) {
 #pragma unroll
         for (int j = 0; j < 3; ++j) s.p[j] = r[4 + j];
 #pragma unroll
@@ -80,7 +80,7 @@ TO_DEV void load_ref_state(const double* __restrict__ ref, int stage, State<KIND
 template <int KIND>
 TO_DEV void dyn_step(const Params& prm, const State<KIND>& x, const double* u, State<KIND>& xn) {
     const double dt = prm.dt;
-    if constexpr (KIND == TRAJOPT_SO3) {
+    if constexpr (on_so3(KIND)) {
         // q+ = q Exp(w dt);  w+ = w + J^-1 (w^T^ J w + u) dt      (traopt_dynamics.py:375-379)
         const double th[3] = {x.xi[0] * dt, x.xi[1] * dt, x.xi[2] * dt};
         double qe[4];
@@ -89,8 +89,22 @@ TO_DEV void dyn_step(const Params& prm, const State<KIND>& x, const double* u, S
         double Jw[3], c[3], r[3], a[3];
         mv3(prm.Ib, x.xi, Jw);
         cross3(x.xi, Jw, c);                 // w^ J w ;  (w^)^T J w = -w x Jw
+        if constexpr (KIND == TRAJOPT_PEND) {
+            // torque = (m g rho) x R^T(-e3) + (m rho) x R^T u,  rho = (0, 0, -l/2)      (traopt_dynamics.py:520-541)
+            const double down[3] = {0.0, 0.0, -1.0};
+            const double mrho[3] = {0.0, 0.0, -0.5 * prm.length * prm.mass};
+            const double mgrho[3] = {0.0, 0.0, mrho[2] * prm.grav};
+            double gb[3], ub[3], t1[3], t2[3];
+            quat_rotate_inv(x.q, down, gb);
+            quat_rotate_inv(x.q, u, ub);
+            cross3(mgrho, gb, t1);
+            cross3(mrho, ub, t2);
 #pragma unroll
-        for (int i = 0; i < 3; ++i) r[i] = u[i] - c[i];
+            for (int i = 0; i < 3; ++i) r[i] = (t1[i] + t2[i]) - c[i];
+        } else {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) r[i] = u[i] - c[i];
+        }
         mv3(prm.Ibinv, r, a);
 #pragma unroll
         for (int i = 0; i < 3; ++i) xn.xi[i] = x.xi[i] + a[i] * dt;
@@ -143,7 +157,7 @@ TO_DEV void dyn_step(const Params& prm, const State<KIND>& x, const double* u, S
 // ------------------------------------------------------------------------------------------
 template <int KIND>
 TO_DEV void tracking_error(const State<KIND>& x, const double* __restrict__ refrow, double* e, double* dxi) {
-    if constexpr (KIND == TRAJOPT_SO3) {
+    if constexpr (on_so3(KIND)) {
         double qe[4];
         quat_compose_inv_r(x.q, refrow, qe);
         so3_log(qe, e);
@@ -190,7 +204,7 @@ TO_DEV double stage_cost(const Params& prm, const State<KIND>& x, const double* 
     double e[NP], dxi[NV];
     tracking_error<KIND>(x, refrow, e, dxi);
     // SO3 quirk 3: the terminal value uses Q
-    const bool useP = terminal && !(KIND == TRAJOPT_SO3 && prm.so3_terminal_quirk);
+    const bool useP = terminal && !(on_so3(KIND) && prm.so3_terminal_quirk);
     const double* W1 = useP ? prm.P1 : prm.W1;
     const double* W2 = useP ? prm.P2 : prm.W2;
     double c = 0.0;
@@ -234,12 +248,12 @@ TO_DEV double cost_expand(const Params& prm, const State<KIND>& x, const double*
     constexpr int NP = Dims<KIND>::NP, NV = Dims<KIND>::NX - Dims<KIND>::NP;
     double e[NP], dxi[NV];
     tracking_error<KIND>(x, refrow, e, dxi);
-    const bool quirk = (KIND == TRAJOPT_SO3) && prm.so3_terminal_quirk;
+    const bool quirk = (on_so3(KIND)) && prm.so3_terminal_quirk;
     const double* W1v = (terminal && !quirk) ? prm.P1 : prm.W1;    // value + gradient
     const double* W2v = (terminal && !quirk) ? prm.P2 : prm.W2;
     const double* W1h = terminal ? prm.P1 : prm.W1;                // Hessian
     double Je[NP * NP];
-    if constexpr (KIND == TRAJOPT_SO3) {
+    if constexpr (on_so3(KIND)) {
         double Ji[9];
         so3_jr_inv(e, Ji);
         mm3(Ji, refrow + 7, Je);                                   // Jr^-1(e) R_ref
@@ -290,7 +304,7 @@ TO_DEV double cost_expand(const Params& prm, const State<KIND>& x, const double*
         double s = 0.0;
 #pragma unroll
         for (int r = 0; r < NP; ++r) {
-            if (KIND != TRAJOPT_SO3 && r < 3 && c >= 3) continue;  // zero block of Je
+            if (!on_so3(KIND) && r < 3 && c >= 3) continue;  // zero block of Je
             s += Je[r * NP + c] * g[r];
         }
         lx[c] = 2.0 * s;
@@ -304,7 +318,7 @@ TO_DEV double cost_expand(const Params& prm, const State<KIND>& x, const double*
             double s = 0.0;
 #pragma unroll
             for (int k = 0; k < NP; ++k) {
-                if (KIND != TRAJOPT_SO3 && k < 3 && c >= 3) continue;
+                if (!on_so3(KIND) && k < 3 && c >= 3) continue;
                 s += W1h[r * NP + k] * Je[k * NP + c];
             }
             M[r * NP + c] = s;
@@ -317,7 +331,7 @@ TO_DEV double cost_expand(const Params& prm, const State<KIND>& x, const double*
             double s = 0.0;
 #pragma unroll
             for (int k = 0; k < NP; ++k) {
-                if (KIND != TRAJOPT_SO3 && k < 3 && r >= 3) continue;
+                if (!on_so3(KIND) && k < 3 && r >= 3) continue;
                 s += Je[k * NP + r] * M[k * NP + c];
             }
             lxx[idx++] = 2.0 * s;
@@ -329,9 +343,9 @@ TO_DEV double cost_expand(const Params& prm, const State<KIND>& x, const double*
 // Dynamics Jacobian blocks (see LinRec in common.cuh for the record layout)
 // ------------------------------------------------------------------------------------------
 template <int KIND>
-TO_DEV void dyn_jacobian(const Params& prm, const State<KIND>& x, double* rec) {
+TO_DEV void dyn_jacobian(const Params& prm, const State<KIND>& x, const double* u, double* rec) {
     const double dt = prm.dt;
-    if constexpr (KIND == TRAJOPT_SO3) {
+    if constexpr (on_so3(KIND)) {
         // [[Exp(w dt)^T, Jr(w dt) dt], [0, I + J^-1 (w^T^ J + s(Jw)) dt]]   (:385-400)
         const double* w = x.xi;
         const double nth[3] = {-w[0] * dt, -w[1] * dt, -w[2] * dt};
@@ -352,6 +366,35 @@ TO_DEV void dyn_jacobian(const Params& prm, const State<KIND>& x, double* rec) {
         mm3(prm.Ibinv, M, H);
 #pragma unroll
         for (int i = 0; i < 9; ++i) rec[18 + i] = ((i % 4 == 0) ? 1.0 : 0.0) + dt * H[i];   // h
+        if constexpr (KIND == TRAJOPT_PEND) {
+            // l = J^-1 (s(m g rho) s(R^T(-e3)) + s(m rho) s(R^T u)) dt          (traopt_dynamics.py:563-577)
+            // bv = J^-1 s(m rho) R^T dt                                          (:590-603)
+            const double down[3] = {0.0, 0.0, -1.0};
+            const double mrho[3] = {0.0, 0.0, -0.5 * prm.length * prm.mass};
+            const double mgrho[3] = {0.0, 0.0, mrho[2] * prm.grav};
+            double gb[3], ub[3], S1[9], S2[9], L1[9], L2[9], Lm[9], Rm[9], Rt[9], B0[9], Bm[9];
+            quat_rotate_inv(x.q, down, gb);
+            quat_rotate_inv(x.q, u, ub);
+            const double Sg[9] = {0, -gb[2], gb[1], gb[2], 0, -gb[0], -gb[1], gb[0], 0};
+            const double Su[9] = {0, -ub[2], ub[1], ub[2], 0, -ub[0], -ub[1], ub[0], 0};
+            skew_mul(mgrho, Sg, S1);
+            skew_mul(mrho, Su, S2);
+#pragma unroll
+            for (int i = 0; i < 9; ++i) L1[i] = S1[i] + S2[i];
+            mm3(prm.Ibinv, L1, Lm);
+#pragma unroll
+            for (int i = 0; i < 9; ++i) rec[27 + i] = Lm[i] * dt;                               // l
+            (void)L2;
+            quat_to_rot(x.q, Rm);
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) Rt[3 * i + j] = Rm[3 * j + i];
+            skew_mul(mrho, Rt, B0);
+            mm3(prm.Ibinv, B0, Bm);
+#pragma unroll
+            for (int i = 0; i < 9; ++i) rec[36 + i] = Bm[i] * dt;                               // bv
+        }
     } else {
         const double* w = x.xi;
         const double* v = x.xi + 3;
@@ -403,7 +446,7 @@ TO_DEV void dyn_jacobian(const Params& prm, const State<KIND>& x, double* rec) {
 // Multiple-shooting defect d = [Log(x_next.q^-1 f.q) ; f.xi - x_next.xi]   (:2882-2888)
 template <int KIND>
 TO_DEV void defect(const State<KIND>& fx, const State<KIND>& xnext, double* d) {
-    if constexpr (KIND == TRAJOPT_SO3) {
+    if constexpr (on_so3(KIND)) {
         double qd[4];
         quat_compose_inv_l(xnext.q, fx.q, qd);
         so3_log(qd, d);

@@ -50,7 +50,7 @@ def receding_horizon(kind, method, *, q_ref, xi_ref, x0_rows, N, T, dt, Ib, mass
     s = BatchSolver(kind, method, N, B, device=device)
     s.set_params(dt=dt, Ib=Ib, mass=mass, Q=Q, R=R, P=P, max_iters=n_iterations, tol_grad_norm=tol_grad_norm,
                  tol_d_norm=tol_d_norm, rollout=rollout, **params)
-    ref_rows = layout.pose_rows(kind == "so3", q_ref)
+    ref_rows = layout.pose_rows(kind in ("so3", "pendulum"), q_ref)
     xs_cl = np.empty((B, T + 1, s.NS))
     us_cl = np.empty((B, T, s.NU))
     J = np.empty((T, B))

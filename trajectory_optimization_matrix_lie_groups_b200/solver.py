@@ -11,10 +11,10 @@ import torch
 from . import _lib
 from ._lib import lib, check
 
-KINDS = {"so3": _lib.SO3, "se3": _lib.SE3, "drone": _lib.DRONE, "rigid": _lib.RIGID}
+KINDS = {"so3": _lib.SO3, "se3": _lib.SE3, "drone": _lib.DRONE, "rigid": _lib.RIGID, "pendulum": _lib.PEND}
 METHODS = {"ss": _lib.SS, "ms": _lib.MS, "al_ms": _lib.AL_MS}
 DIMS = {  # kind -> (NX, NP, NU, NS)
-    "so3": (6, 3, 3, 7), "se3": (12, 6, 6, 13), "drone": (12, 6, 4, 13), "rigid": (12, 6, 6, 13),
+    "so3": (6, 3, 3, 7), "se3": (12, 6, 6, 13), "drone": (12, 6, 4, 13), "rigid": (12, 6, 6, 13), "pendulum": (6, 3, 3, 7),
 }
 
 
@@ -29,7 +29,7 @@ def _stream(device):
 class BatchSolver:
     """B independent tracking problems of one family, solved together on one GPU.
 
-    kind: 'so3' | 'se3' | 'drone' | 'rigid';  method: 'ss' | 'ms' | 'al_ms'.
+    kind: 'so3' | 'se3' | 'drone' | 'rigid' | 'pendulum';  method: 'ss' | 'ms' | 'al_ms'.
     """
 
     def __init__(self, kind, method, N, B, device=None):
@@ -64,13 +64,14 @@ class BatchSolver:
     def set_params(self, *, dt, Ib, mass, Q, R, P, gravity=9.8, max_iters=100, tol_grad_norm=1e-6,
                    tol_d_norm=1e-6, max_reg=1e10, rollout="nonlinear", line_search=False, n_alphas=0,
                    defect_kappa=0.0, lb=None, ub=None, n_al_iters=100, al_mu0=1e-2, al_mu_scale=10.0,
-                   al_mu_max=1e8, tol_constr=1e-2):
+                   al_mu_max=1e8, tol_constr=1e-2, length=0.0):
         NX, NU = self.NX, self.NU
         p = _lib.Params()
         p.dt = float(dt)
         p.Ib[:] = np.asarray(Ib, dtype=np.float64).reshape(9).tolist()
         p.mass = float(mass)
         p.gravity = float(gravity)
+        p.length = float(length)
         for name, M, n in (("Q", Q, NX), ("P", P, NX), ("R", R, NU)):
             M = np.asarray(M, dtype=np.float64)
             if M.shape != (n, n):

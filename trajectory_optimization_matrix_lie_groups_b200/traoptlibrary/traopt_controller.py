@@ -121,10 +121,7 @@ class _NativeController(BaseController):
         else:
             if bounds is not None:
                 params["lb"], params["ub"] = bounds
-            kind = self._kind
-            s.set_params(dt=self.dynamics.dt, Ib=self.dynamics.J if kind == "so3" else self.dynamics.Ib,
-                         mass=1.0 if kind == "so3" else self.dynamics.m, gravity=getattr(self.dynamics, "g", 9.8),
-                         Q=cost.Q, R=cost.R, P=cost.P, **params)
+            s.set_params(Q=cost.Q, R=cost.R, P=cost.P, **_native.dynamics_params(self._kind, self.dynamics), **params)
         return s
 
     def _params(self, n_iterations, tol_grad_norm, tol_d_norm=1e-6):
@@ -133,7 +130,7 @@ class _NativeController(BaseController):
                     line_search=self._line_search)
 
     def _alphas(self):
-        n = self.N_ALPHAS_SS if self.METHOD == "ss" else (13 if self._kind == "so3" else 20)
+        n = self.N_ALPHAS_SS if self.METHOD == "ss" else (13 if self._kind in ("so3", "pendulum") else 20)
         return 1.1 ** (-np.arange(n) ** 2)
 
     def _x0_rows(self, x0_batch):

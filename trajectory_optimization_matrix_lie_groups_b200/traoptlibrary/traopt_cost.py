@@ -46,7 +46,7 @@ def _placeholder_cost(nx, nu):
 
 class _PlaceholderDynamics:
     def __init__(self, kind):
-        self.J = np.eye(3) if kind == "so3" else np.eye(6)
+        self.J = np.eye(3) if kind in ("so3", "pendulum") else np.eye(6)
         self.Ib = np.eye(3)
         self.m = 1.0
         self.dt = 1.0

@@ -80,7 +80,7 @@ class _NativeDynamics(BaseDynamics):
             from .traopt_cost import _placeholder_cost
             nx = self._state_size
             cost = _placeholder_cost(nx, self._action_size)
-            if self.KIND == "so3":
+            if self.KIND in ("so3", "pendulum"):
                 q_ref, xi_ref = np.tile(np.array([0.0, 0, 0, 1]), (2, 1)), np.zeros((2, 3))
             else:
                 q_ref, xi_ref = np.tile(np.eye(4), (2, 1, 1)), np.zeros((2, 6))
@@ -113,6 +113,23 @@ class SO3Dynamics(_NativeDynamics):
     def __init__(self, J, dt, integration_method="euler", state_size=(3, 3), action_size=3, hessians=False,
                  debug=None, **kwargs):
         self._init_common(J, dt, integration_method, state_size, action_size, hessians, debug)
+
+
+class Pendulum3dDyanmics(_NativeDynamics):
+    """3-D pendulum on SO(3) actuated by a force at the pivot (traopt_dynamics.py:421-626; the class name,
+    typo included, is the reference's)."""
+    KIND = "pendulum"
+
+    def __init__(self, J, m, length, dt, integration_method="euler", state_size=(3, 3), action_size=3, hessians=False,
+                 debug=None, **kwargs):
+        self._init_common(J, dt, integration_method, state_size, action_size, hessians, debug)
+        self._m = float(m)
+        self._l = float(length)
+        self._g = 9.8                                         # :460
+
+    m = property(lambda self: self._m)
+    l = property(lambda self: self._l)
+    g = property(lambda self: self._g)
 
 
 class SE3Dynamics(_NativeDynamics):

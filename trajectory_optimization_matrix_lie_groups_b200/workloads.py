@@ -54,7 +54,7 @@ class Workload:
 
     @property
     def mass(self):
-        return 1.0 if self.kind == "so3" else float(self.J[4, 4])
+        return 1.0 if self.kind in ("so3", "pendulum") else float(self.J[4, 4])
 
     def make_solver(self, B=None, device=None, offset=0):
         """BatchSolver configured for problems [offset, offset+B) of this workload, and their x0 rows."""
@@ -65,7 +65,7 @@ class Workload:
         if self.bounds is not None:
             kw["lb"], kw["ub"] = self.bounds
         s.set_params(dt=self.dt, Ib=self.Ib, mass=self.mass, Q=self.Q, R=self.R, P=self.P, **kw)
-        s.set_reference(layout.pose_rows(self.kind == "so3", self.q_ref), self.xi_ref)
+        s.set_reference(layout.pose_rows(self.kind in ("so3", "pendulum"), self.q_ref), self.xi_ref)
         return s, self.x0_rows[offset:offset + B]
 
 
