@@ -1,354 +1,30 @@
 // C ABI of the batched DDP/iLQR solver (see include/trajopt_b200.h for the contract and the
 // reference call each entry point stands for).  Host side only orchestrates kernel launches on
-// one stream; every number is produced by the kernels in kernels.cuh / kernels_fwd.cuh.
-#include <atomic>
-#include <cmath>
-#include <cstdio>
-#include <cstring>
-#include <new>
-#include <vector>
+// one stream; every number is produced by the kernels.  The kernel sequences of each problem family
+// are instantiated in kind_<family>.cu (host_impl.cuh), this file only dispatches.
+#include "host_impl.cuh"
 
-#include <cstdlib>
+TRAJOPT_KIND_EXTERN(TRAJOPT_SO3)
+TRAJOPT_KIND_EXTERN(TRAJOPT_SE3)
+TRAJOPT_KIND_EXTERN(TRAJOPT_DRONE)
+TRAJOPT_KIND_EXTERN(TRAJOPT_RIGID)
+TRAJOPT_KIND_EXTERN(TRAJOPT_PEND)
 
-#include "kernels_fwd.cuh"
-#include "debug.cuh"
-
-using namespace trajopt;
+using namespace trajopt_host;
 
 // ------------------------------------------------------------------------------------------
 // error reporting / launch accounting
 // ------------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
-static std::atomic<long long> g_launches{0};
+std::atomic<long long> g_trajopt_launches{0};
 
 extern "C" int trajopt_set_error_(cudaError_t e, const char* file, int line) {
     snprintf(g_err, sizeof(g_err), "CUDA error %d (%s) at %s:%d", (int)e, cudaGetErrorString(e), file, line);
     return TRAJOPT_E_CUDA;
 }
-static int fail(int code, const char* msg) {
+int trajopt_fail_(int code, const char* msg) {
     snprintf(g_err, sizeof(g_err), "%s", msg);
     return code;
-}
-
-#define LAUNCH(kern, grid, block, smem, stream, ...)                 \
-    do {                                                             \
-        kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);    \
-        g_launches.fetch_add(1, std::memory_order_relaxed);          \
-        CUDA_OK(cudaPeekAtLastError());                              \
-    } while (0)
-
-enum { PH_LIN = 0, PH_BWD = 1, PH_FWD = 2, PH_OTHER = 3, PH_COUNT = 4 };
-
-struct trajopt_handle {
-    int kind = 0, method = 0, N = 0, B = 0, Bp = 0, device = 0;
-    int NX = 0, NP = 0, NU = 0, NS = 0, LEN = 0, REFROW = 0;
-    Params prm{};
-    Work w{};
-    trajopt_params user{};
-    bool have_params = false, have_ref = false, begun = false;
-    int it = 0;              // next inner iteration
-    bool inner_done = true;  // the inner loop of the current fit() / AL outer iteration has ended
-    int al_outer = 0;        // AL outer iterations completed
-    bool al_finished = false;
-    int hist_cap = -1, cand_rows = -1;
-    std::vector<void*> allocs;
-    void* hist_allocs[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    double* d_ref = nullptr;
-    double* d_dweight = nullptr;
-    int* h_counters = nullptr;   // pinned
-    // host staging for trajopt_solve_host
-    double *s_x0 = nullptr, *s_us0 = nullptr, *s_xs = nullptr, *s_us = nullptr, *s_J = nullptr, *s_grad = nullptr, *s_def = nullptr;
-    int32_t *s_iters = nullptr, *s_status = nullptr;
-    size_t s_us0_bytes = 0;
-    // phase profiling
-    bool profiling = false;
-    cudaEvent_t ev[2] = {nullptr, nullptr};
-    double phase_ms[PH_COUNT] = {0, 0, 0, 0};
-    long long phase_cnt[PH_COUNT] = {0, 0, 0, 0};
-};
-
-namespace {
-
-struct DeviceGuard {
-    int prev = -1;
-    bool ok = true;
-    explicit DeviceGuard(int dev) {
-        if (cudaGetDevice(&prev) != cudaSuccess) ok = false;
-        if (ok && prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
-    }
-    ~DeviceGuard() {
-        if (prev >= 0) cudaSetDevice(prev);
-    }
-};
-
-template <typename T>
-int dalloc(trajopt_handle* h, T** p, size_t count, bool zero = true) {
-    void* q = nullptr;
-    CUDA_OK(cudaMalloc(&q, count * sizeof(T)));
-    if (zero) CUDA_OK(cudaMemset(q, 0, count * sizeof(T)));
-    h->allocs.push_back(q);
-    *p = (T*)q;
-    return 0;
-}
-
-struct PhaseTimer {
-    trajopt_handle* h;
-    cudaStream_t s;
-    int ph;
-    PhaseTimer(trajopt_handle* h_, cudaStream_t s_, int ph_) : h(h_), s(s_), ph(ph_) {
-        if (h->profiling) cudaEventRecord(h->ev[0], s);
-    }
-    ~PhaseTimer() {
-        if (h->profiling) {
-            cudaEventRecord(h->ev[1], s);
-            cudaEventSynchronize(h->ev[1]);
-            float ms = 0.f;
-            cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
-            h->phase_ms[ph] += ms;
-            h->phase_cnt[ph] += 1;
-        }
-    }
-};
-
-inline int blocks_for(int n, int bs) { return (n + bs - 1) / bs; }
-
-// host copies of the small algebra needed to pack parameters
-void inv3(const double* A, double* Ai) {
-    const double a = A[0], b = A[1], c = A[2], d = A[3], e = A[4], f = A[5], g = A[6], hh = A[7], i = A[8];
-    const double det = a * (e * i - f * hh) - b * (d * i - f * g) + c * (d * hh - e * g);
-    const double id = 1.0 / det;
-    Ai[0] = (e * i - f * hh) * id; Ai[1] = (c * hh - b * i) * id; Ai[2] = (b * f - c * e) * id;
-    Ai[3] = (f * g - d * i) * id;  Ai[4] = (a * i - c * g) * id;  Ai[5] = (c * d - a * f) * id;
-    Ai[6] = (d * hh - e * g) * id; Ai[7] = (b * g - a * hh) * id; Ai[8] = (a * e - b * d) * id;
-}
-void host_quat_to_rot(const double* q, double* R) {
-    const double x = q[0], y = q[1], z = q[2], w = q[3];
-    const double tx = 2.0 * x, ty = 2.0 * y, tz = 2.0 * z;
-    const double twx = tx * w, twy = ty * w, twz = tz * w;
-    const double txx = tx * x, txy = ty * x, txz = tz * x;
-    const double tyy = ty * y, tyz = tz * y, tzz = tz * z;
-    R[0] = 1.0 - (tyy + tzz); R[1] = txy - twz;         R[2] = txz + twy;
-    R[3] = txy + twz;         R[4] = 1.0 - (txx + tzz); R[5] = tyz - twx;
-    R[6] = txz - twy;         R[7] = tyz + twx;         R[8] = 1.0 - (txx + tyy);
-}
-
-// ------------------------------------------------------------------------------------------
-// kernel sequences, templated on the problem family
-// ------------------------------------------------------------------------------------------
-template <int KIND, bool MS>
-int run_linearize(trajopt_handle* h, cudaStream_t s) {
-    PhaseTimer t(h, s, PH_LIN);
-    dim3 grid(blocks_for(h->Bp, 128), h->N + 1);
-    LAUNCH((k_linearize<KIND, MS>), grid, 128, 0, s, h->prm, h->w);
-    return 0;
-}
-
-// TRAJOPT_BACKWARD=1 selects the one-warp-per-group sweep for the 12-dimensional families too (A/B measurements)
-static bool use_one_warp_sweep() {
-    static const bool v = [] { const char* e = getenv("TRAJOPT_BACKWARD"); return e && e[0] == '1'; }();
-    return v;
-}
-
-template <int KIND, bool MS>
-int run_backward(trajopt_handle* h, cudaStream_t s, int it) {
-    PhaseTimer t(h, s, PH_BWD);
-    if constexpr (!on_so3(KIND)) {
-        if (!use_one_warp_sweep()) {
-            constexpr size_t smem3 = B3Smem<KIND>::BYTES;
-            CUDA_OK(cudaFuncSetAttribute(k_backward3<KIND, MS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
-            LAUNCH((k_backward3<KIND, MS>), h->Bp / 32, kB3Threads, smem3, s, h->prm, h->w, it);
-            return 0;
-        }
-    }
-    constexpr size_t smem = (size_t)bwd_smem_doubles<KIND>() * kBlock * sizeof(double);
-    CUDA_OK(cudaFuncSetAttribute(k_backward<KIND, MS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    LAUNCH((k_backward<KIND, MS>), h->Bp / kBlock, kBlock, smem, s, h->prm, h->w, it);
-    return 0;
-}
-
-template <int KIND, bool MS, bool WRITE, bool COST>
-int run_forward(trajopt_handle* h, cudaStream_t s, int a_lo, int a_cnt, int need, int from_state) {
-    PhaseTimer t(h, s, PH_FWD);
-    const int grid = blocks_for(h->Bp * a_cnt, kBlock);
-    if (h->prm.rollout_linear)
-        LAUNCH((k_forward<KIND, MS, true, WRITE, COST>), grid, kBlock, 0, s, h->prm, h->w, a_lo, a_cnt, need, from_state);
-    else
-        LAUNCH((k_forward<KIND, MS, false, WRITE, COST>), grid, kBlock, 0, s, h->prm, h->w, a_lo, a_cnt, need, from_state);
-    return 0;
-}
-
-// number of problems still running -> host (synchronises the stream)
-int count_running(trajopt_handle* h, cudaStream_t s, int* out) {
-    PhaseTimer t(h, s, PH_OTHER);
-    CUDA_OK(cudaMemsetAsync(h->w.counters, 0, 4 * sizeof(int), s));
-    LAUNCH(k_count_running, blocks_for(h->Bp, 128), 128, 0, s, h->prm, h->w);
-    CUDA_OK(cudaMemcpyAsync(h->h_counters, h->w.counters, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
-    CUDA_OK(cudaStreamSynchronize(s));
-    *out = h->h_counters[0];
-    return 0;
-}
-
-// one pass of the `for iteration in range(n_iterations)` body for every running problem
-template <int KIND>
-int inner_iteration(trajopt_handle* h, cudaStream_t s) {
-    const int it = h->it;
-    const int na = h->prm.n_alphas;
-    const int bgrid = blocks_for(h->Bp, 128);
-    int rc;
-    if (h->method == TRAJOPT_SS) {
-        if ((rc = run_linearize<KIND, false>(h, s))) return rc;
-        if ((rc = run_backward<KIND, false>(h, s, it))) return rc;
-        // line search (:1972-1990): step size 0 first (accepted by nearly every problem), then
-        // all remaining step sizes at once for the problems that rejected it
-        if ((rc = run_forward<KIND, false, true, true>(h, s, 0, 1, -2, 0))) return rc;
-        LAUNCH(k_ls_select_ss, bgrid, 128, 0, s, h->prm, h->w, it, 0, 1, na == 1 ? 1 : 0);
-        if (na > 1) {
-            if ((rc = run_forward<KIND, false, false, true>(h, s, 1, na - 1, -1, 0))) return rc;
-            LAUNCH(k_ls_select_ss, bgrid, 128, 0, s, h->prm, h->w, it, 1, na - 1, 1);
-            if ((rc = run_forward<KIND, false, true, false>(h, s, 1, 1, -3, 1))) return rc;
-        }
-        LAUNCH(k_ls_commit_ss, bgrid, 128, 0, s, h->prm, h->w, it);
-    } else {
-        if ((rc = run_linearize<KIND, true>(h, s))) return rc;
-        if ((rc = run_backward<KIND, true>(h, s, it))) return rc;
-        if (it < h->prm.max_iters) {
-            if (h->prm.line_search) {
-                {
-                    PhaseTimer t(h, s, PH_FWD);
-                    LAUNCH((k_ms_expected<KIND>), h->Bp / kBlock, kBlock, 0, s, h->prm, h->w, h->d_dweight);
-                }
-                if ((rc = run_forward<KIND, true, true, true>(h, s, 0, 1, -2, 0))) return rc;
-                LAUNCH(k_ls_select_ms, bgrid, 128, 0, s, h->prm, h->w, it, 0, 1, na == 1 ? 1 : 0);
-                if (na > 1) {
-                    if ((rc = run_forward<KIND, true, false, true>(h, s, 1, na - 1, -1, 0))) return rc;
-                    LAUNCH(k_ls_select_ms, bgrid, 128, 0, s, h->prm, h->w, it, 1, na - 1, 1);
-                    if ((rc = run_forward<KIND, true, true, false>(h, s, 1, 1, -3, 1))) return rc;
-                }
-                LAUNCH(k_ls_commit_ms, bgrid, 128, 0, s, h->prm, h->w, it);
-            } else {
-                if (h->prm.rollout_linear) {
-                    if ((rc = run_forward<KIND, true, true, false>(h, s, 0, 1, -2, 0))) return rc;
-                } else {
-                    PhaseTimer t(h, s, PH_FWD);
-                    constexpr size_t fsmem = FwdSmem<KIND>::BYTES;
-                    CUDA_OK(cudaFuncSetAttribute(k_forward_ms_full<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-                    LAUNCH((k_forward_ms_full<KIND>), h->Bp / kBlock, kBlock, fsmem, s, h->prm, h->w);
-                }
-                LAUNCH(k_accept_all, bgrid, 128, 0, s, h->prm, h->w, it);
-            }
-        }
-    }
-    h->it = it + 1;
-    return 0;
-}
-
-// run the inner loop for up to n_iters iterations; *active = problems still running
-template <int KIND>
-int run_inner(trajopt_handle* h, cudaStream_t s, int n_iters, int* active) {
-    // MS needs one closing pass after the last rollout (cost / defect of the final trajectory)
-    const int last = (h->method == TRAJOPT_SS) ? h->prm.max_iters : h->prm.max_iters + 1;
-    int rc, act = -1;
-    for (int j = 0; j < n_iters && h->it < last; ++j) {
-        if ((rc = inner_iteration<KIND>(h, s))) return rc;
-        if ((rc = count_running(h, s, &act))) return rc;
-        if (act == 0) break;
-    }
-    if (act < 0 && (rc = count_running(h, s, &act))) return rc;
-    if (act == 0 || h->it >= last) h->inner_done = true;
-    *active = act;
-    return 0;
-}
-
-template <int KIND>
-int start_inner(trajopt_handle* h, cudaStream_t s, bool al_restart) {
-    PhaseTimer t(h, s, PH_OTHER);
-    const int bgrid = blocks_for(h->Bp, 128);
-    if (al_restart) LAUNCH(k_reset_al_inner, bgrid, 128, 0, s, h->prm, h->w);
-    else LAUNCH(k_reset, bgrid, 128, 0, s, h->prm, h->w);
-    if (h->method == TRAJOPT_SS) {
-        LAUNCH((k_init_ss<KIND>), h->Bp / kBlock, kBlock, 0, s, h->prm, h->w);
-    } else {
-        dim3 grid(bgrid, h->N + 1);
-        LAUNCH((k_init_ms<KIND>), grid, 128, 0, s, h->prm, h->w, al_restart);
-        if (h->prm.line_search) {
-            std::vector<double> dw((size_t)h->Bp, h->prm.defect_mu0);
-            CUDA_OK(cudaMemcpyAsync(h->d_dweight, dw.data(), dw.size() * sizeof(double), cudaMemcpyHostToDevice, s));
-            CUDA_OK(cudaStreamSynchronize(s));
-        }
-    }
-    h->it = 0;
-    h->inner_done = false;
-    return 0;
-}
-
-template <int KIND>
-int begin_impl(trajopt_handle* h, const double* d_x0, const double* d_us_init, int us_mode, cudaStream_t s) {
-    h->w.us_init = d_us_init;
-    h->w.us_mode = d_us_init ? us_mode : 0;
-    LAUNCH((k_load_x0<KIND>), blocks_for(h->Bp, 128), 128, 0, s, h->prm, h->w, d_x0);
-    if (h->method == TRAJOPT_AL_MS) {
-        dim3 grid(blocks_for(h->Bp, 128), h->N + 1);
-        LAUNCH((k_al_init<KIND>), grid, 128, 0, s, h->prm, h->w, h->user.al_mu0);
-    }
-    h->al_outer = 0;
-    h->al_finished = false;
-    int rc = start_inner<KIND>(h, s, false);
-    if (rc) return rc;
-    h->begun = true;
-    return 0;
-}
-
-template <int KIND>
-int iterate_impl(trajopt_handle* h, int n_iters, int* n_active_out, cudaStream_t s) {
-    int rc, act = 0;
-    if (h->method != TRAJOPT_AL_MS) {
-        if (h->inner_done) {
-            if ((rc = count_running(h, s, &act))) return rc;
-        } else if ((rc = run_inner<KIND>(h, s, n_iters, &act))) return rc;
-        if (n_active_out) *n_active_out = act;
-        return 0;
-    }
-    // augmented Lagrangian: one unit = one outer iteration (:3231-3264)
-    int remaining = 1;
-    for (int j = 0; j < n_iters && !h->al_finished; ++j) {
-        if (h->inner_done) {
-            if ((rc = start_inner<KIND>(h, s, true))) return rc;   // cold restart (:3237)
-        }
-        if ((rc = run_inner<KIND>(h, s, h->prm.max_iters + 1, &act))) return rc;
-        {
-            PhaseTimer t(h, s, PH_OTHER);
-            CUDA_OK(cudaMemsetAsync(h->w.counters, 0, 4 * sizeof(int), s));
-            LAUNCH((k_al_update<KIND>), blocks_for(h->Bp, 128), 128, 0, s, h->prm, h->w, h->user.tol_constr,
-                   h->user.al_mu_scale, h->user.al_mu_max, h->al_outer);
-            CUDA_OK(cudaMemcpyAsync(h->h_counters, h->w.counters, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
-            CUDA_OK(cudaStreamSynchronize(s));
-        }
-        remaining = h->h_counters[2];
-        h->al_outer += 1;
-        if (remaining == 0 || h->al_outer >= h->user.n_al_iters) h->al_finished = true;
-    }
-    if (n_active_out) *n_active_out = h->al_finished ? 0 : remaining;
-    return 0;
-}
-
-template <int KIND>
-int debug_linearize_impl(trajopt_handle* h, double* Fx, double* Fu, double* dd, double* L, double* Lx, double* Lxx,
-                         double* Lu, cudaStream_t s) {
-    int rc;
-    if (h->method == TRAJOPT_SS) rc = run_linearize<KIND, false>(h, s);
-    else rc = run_linearize<KIND, true>(h, s);
-    if (rc) return rc;
-    dim3 grid(blocks_for(h->B, 128), h->N + 1);
-    LAUNCH((k_export_lin<KIND>), grid, 128, 0, s, h->prm, h->w, Fx, Fu, dd, L, Lx, Lxx, Lu);
-    return 0;
-}
-
-template <int KIND>
-int debug_stage_impl(trajopt_handle* h, int i, int terminal, int n, const double* x, const double* u, double* f,
-                     double* Fx, double* Fu, double* l, double* lx, double* lxx, double* lu, double* err, cudaStream_t s) {
-    LAUNCH((k_debug_stage<KIND>), blocks_for(n, 64), 64, 0, s, h->prm, h->d_ref, i, terminal, n, x, u, f, Fx, Fu, l, lx,
-           lxx, lu, err);
-    return 0;
 }
 
 #define DISPATCH_KIND(h, fn, ...)                                             \
@@ -358,32 +34,6 @@ int debug_stage_impl(trajopt_handle* h, int i, int terminal, int n, const double
      : (h)->kind == TRAJOPT_RIGID ? fn<TRAJOPT_RIGID>(__VA_ARGS__)            \
                                   : fn<TRAJOPT_PEND>(__VA_ARGS__))
 
-int ensure_hist(trajopt_handle* h) {
-    const int cap = h->prm.max_iters;
-    const int rows = (h->method == TRAJOPT_SS) ? h->prm.n_alphas : 2 * h->prm.n_alphas + 4;
-    if (cap == h->hist_cap && rows == h->cand_rows) return 0;
-    for (void*& p : h->hist_allocs) {
-        if (p) cudaFree(p);
-        p = nullptr;
-    }
-    const size_t Bp = (size_t)h->Bp;
-    const size_t sz[5] = {(size_t)(cap > 0 ? cap : 1) * Bp * 8, (size_t)(cap + 1) * Bp * 8, (size_t)(cap + 1) * Bp * 8,
-                          (size_t)(cap > 0 ? cap : 1) * Bp * 4, (size_t)rows * Bp * 8};
-    for (int i = 0; i < 5; ++i) {
-        CUDA_OK(cudaMalloc(&h->hist_allocs[i], sz[i]));
-        CUDA_OK(cudaMemset(h->hist_allocs[i], 0, sz[i]));
-    }
-    h->w.Jhist = (double*)h->hist_allocs[0];
-    h->w.gradhist = (double*)h->hist_allocs[1];
-    h->w.defhist = (double*)h->hist_allocs[2];
-    h->w.alphahist = (int*)h->hist_allocs[3];
-    h->w.Jcand = (double*)h->hist_allocs[4];
-    h->hist_cap = cap;
-    h->cand_rows = rows;
-    return 0;
-}
-
-}  // namespace
 
 // ------------------------------------------------------------------------------------------
 // exported entry points
@@ -394,8 +44,8 @@ const char* trajopt_last_error(void) { return g_err; }
 int trajopt_version(void) { return 100; }
 
 int64_t trajopt_launch_count(int reset) {
-    const long long v = g_launches.load();
-    if (reset) g_launches.store(0);
+    const long long v = g_trajopt_launches.load();
+    if (reset) g_trajopt_launches.store(0);
     return (int64_t)v;
 }
 

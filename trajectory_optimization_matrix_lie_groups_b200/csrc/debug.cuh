@@ -38,7 +38,7 @@ __device__ inline void put_block(double* M6, int br, int bc, const double* B3, d
         for (int j = 0; j < 3; ++j) M6[(3 * br + i) * 6 + 3 * bc + j] = sign * B3[3 * i + j];
 }
 
-__global__ void k_debug_lie(int op, int n, const double* __restrict__ in, double* __restrict__ out) {
+static __global__ void k_debug_lie(int op, int n, const double* __restrict__ in, double* __restrict__ out) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n) return;
     const double* x = in + (size_t)r * lie_in_width(op);
@@ -212,7 +212,7 @@ __global__ void k_debug_stage(const Params prm, const double* __restrict__ ref, 
 
 // FP64 FMA peak: 8 independent dependent-chains of DFMA per thread, enough warps to fill every SM.
 // 2 flop per DFMA; the result is stored so the chains cannot be removed.
-__global__ void __launch_bounds__(256) k_fp64_peak(int iters, double seed, double* __restrict__ sink) {
+static __global__ void __launch_bounds__(256) k_fp64_peak(int iters, double seed, double* __restrict__ sink) {
     double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
     const double m = 0.999999, c = 1e-9;
     for (int i = 0; i < iters; ++i) {

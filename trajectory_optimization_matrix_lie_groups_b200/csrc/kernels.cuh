@@ -204,7 +204,7 @@ __global__ void k_load_x0(const Params prm, Work w, const double* __restrict__ x
 }
 
 // reset per-fit state (regulariser :1899-1900, histories)
-__global__ void k_reset(const Params prm, Work w) {
+static __global__ void k_reset(const Params prm, Work w) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= prm.Bp) return;
     w.sel[b] = 0;
@@ -222,7 +222,7 @@ __global__ void k_reset(const Params prm, Work w) {
 }
 
 // only the problems whose AL outer loop is still running are restarted
-__global__ void k_reset_al_inner(const Params prm, Work w) {
+static __global__ void k_reset_al_inner(const Params prm, Work w) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= prm.Bp) return;
     if (b < prm.B && !w.al_done[b]) {

@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(kBlock) k_forward_ms_full(const Params prm, Wo
 }
 
 // MS without line search: alpha = 1 is always accepted (:2592-2600)
-__global__ void k_accept_all(const Params prm, Work w, int it) {
+static __global__ void k_accept_all(const Params prm, Work w, int it) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= prm.B || w.status[b] != TRAJOPT_RUNNING) return;
     w.sel[b] = 1 - w.sel[b];
@@ -301,7 +301,7 @@ __global__ void k_accept_all(const Params prm, Work w, int it) {
 }
 
 // count problems that are still running into counters[0]
-__global__ void k_count_running(const Params prm, Work w) {
+static __global__ void k_count_running(const Params prm, Work w) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     const bool run = (b < prm.B) && (w.status[b] == TRAJOPT_RUNNING);
     const unsigned m = __ballot_sync(0xffffffffu, run);
@@ -311,7 +311,7 @@ __global__ void k_count_running(const Params prm, Work w) {
 // SS line search (:1972-1990): examine candidates [a_lo, a_lo+a_cnt) in index order, accept the
 // first J_new < J_opt.  first pass (a_lo == 0): the accepted trajectory is already in the other
 // buffer; later passes only pick the index and a final k_forward<WRITE> materialises it.
-__global__ void k_ls_select_ss(const Params prm, Work w, int it, int a_lo, int a_cnt, int last) {
+static __global__ void k_ls_select_ss(const Params prm, Work w, int it, int a_lo, int a_cnt, int last) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     const bool in = (b < prm.B) && (w.status[b] == TRAJOPT_RUNNING);
     bool pending = false;
@@ -340,7 +340,7 @@ __global__ void k_ls_select_ss(const Params prm, Work w, int it, int a_lo, int a
 }
 
 // commit an accepted SS candidate whose trajectory is in the other buffer
-__global__ void k_ls_commit_ss(const Params prm, Work w, int it) {
+static __global__ void k_ls_commit_ss(const Params prm, Work w, int it) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= prm.B || w.status[b] != TRAJOPT_RUNNING) return;
     const int a = w.ls_state[b];
@@ -476,7 +476,7 @@ __global__ void __launch_bounds__(kBlock) k_ms_expected(const Params prm, Work w
 }
 
 // accept the first alpha with merit_new - merit < gamma (dJ_exp(alpha) - alpha w ||d||) (:2576)
-__global__ void k_ls_select_ms(const Params prm, Work w, int it, int a_lo, int a_cnt, int last) {
+static __global__ void k_ls_select_ms(const Params prm, Work w, int it, int a_lo, int a_cnt, int last) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     const bool in = (b < prm.B) && (w.status[b] == TRAJOPT_RUNNING);
     bool pending = false;
@@ -513,7 +513,7 @@ __global__ void k_ls_select_ms(const Params prm, Work w, int it, int a_lo, int a
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(&w.counters[1], __popc(m));
 }
 
-__global__ void k_ls_commit_ms(const Params prm, Work w, int it) {
+static __global__ void k_ls_commit_ms(const Params prm, Work w, int it) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= prm.B || w.status[b] != TRAJOPT_RUNNING) return;
     const int a = w.ls_state[b];
@@ -598,7 +598,7 @@ __global__ void k_al_init(const Params prm, Work w, double mu0) {
 // Layout exports: SoA [stage][field][Bp] -> problem-major
 // ------------------------------------------------------------------------------------------
 // out[b][stage][f] = src_sel[b][stage][f][b]   (grid.y = stage)
-__global__ void k_export_traj(int B, int Bp, int F, const double* s0, const double* s1, const int* sel, double* out, int nstage) {
+static __global__ void k_export_traj(int B, int Bp, int F, const double* s0, const double* s1, const int* sel, double* out, int nstage) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     const int stage = blockIdx.y;
     if (b >= B) return;

@@ -1,0 +1,4 @@
+// Kernel sequences of one problem family (explicit instantiation; see host_impl.cuh)
+#include "host_impl.cuh"
+
+TRAJOPT_KIND_INSTANTIATE(TRAJOPT_SE3)
