@@ -163,3 +163,28 @@ def test_reference_file_formats_roundtrip(tmp_path):
     assert set(d) == {"prob", "ms_se3", "ss_se3"} and set(d["prob"]) == {"J", "dt", "q_ref", "xi_ref", "x0", "Q", "P", "R"}
     assert len(d["ms_se3"]["xs"]) == 21 and np.array_equal(d["ms_se3"]["xs"][3][0], q[3])
     assert "defect_hist" not in d["ss_se3"] and d["ms_se3"]["J_hist"] == [3.0, 2.0]
+
+
+def test_utilis_converters_and_lie_helpers():
+    """traopt_utilis mirror: hat/vee/ad maps and the manif converters (traopt_utilis.py:13-92, 331-399)."""
+    from trajectory_optimization_matrix_lie_groups_b200.traoptlibrary import traopt_utilis as tu
+    rng = np.random.default_rng(1)
+    xi = rng.standard_normal(6)
+    assert np.array_equal(tu.unskew(tu.skew(xi[:3])), xi[:3])
+    assert np.array_equal(tu.se3_vee(tu.se3_hat(xi)), xi)
+    ad = tu.adjoint(xi)
+    assert np.array_equal(ad[:3, :3], tu.skew(xi[:3])) and np.array_equal(ad[3:, :3], tu.skew(xi[3:])) and np.all(ad[:3, 3:] == 0)
+    assert np.array_equal(tu.coadjoint(xi), ad.T)
+    T = np.eye(4)
+    T[:3, :3] = Rotation.from_rotvec([0.3, -0.2, 0.9]).as_matrix()
+    T[:3, 3] = [1.0, 2.0, 3.0]
+    m = tu.SE32manifSE3(T)
+    assert np.allclose(m.translation(), [1, 2, 3]) and abs(np.linalg.norm(m.quat()) - 1) < 1e-15
+    assert np.max(np.abs(tu.manifSE32SE3(m) - T)) < 1e-15
+    t = tu.se32manifse3(xi)
+    assert np.array_equal(t.coeffs(), np.concatenate((xi[3:], xi[:3]))) and np.array_equal(tu.manifse32se3(t), xi)
+    J = rng.standard_normal((6, 6))
+    P = np.block([[np.zeros((3, 3)), np.eye(3)], [np.eye(3), np.zeros((3, 3))]])
+    assert np.array_equal(tu.Jmnf2J(J), P @ J @ P)
+    assert tu.is_pos_def(np.eye(3)) and not tu.is_pos_def(-np.eye(3)) and not tu.is_pos_def(np.array([[1.0, 2.0], [0.0, 1.0]]))
+    assert abs(tu.SE32absangle(T) - np.rad2deg(np.linalg.norm([0.3, -0.2, 0.9]))) < 1e-10

@@ -1,4 +1,4 @@
-"""Minimal stand-ins for the two manifpy types that cross the reference's SO(3) API.
+"""Minimal stand-ins for the manifpy types that cross the reference's API.
 
 The reference hands `manifpy.SO3` / `manifpy.SO3Tangent` objects to and from the SO3 controllers
 (benchmark_SO3_tracking.py:67-79, 194-201: `x[0].rotation()`, `x[1].coeffs()`).  manifpy is a
@@ -79,3 +79,49 @@ def so3_vel(w):
     if hasattr(w, "coeffs"):
         return np.asarray(w.coeffs(), dtype=float).reshape(3)
     return np.asarray(w, dtype=float).reshape(3)
+
+
+class SE3:
+    """Pose as (position, unit quaternion [x, y, z, w]) — what `SE32manifSE3` builds (traopt_utilis.py:331-342)."""
+
+    def __init__(self, position=None, quaternion=None):
+        p = np.zeros(3) if position is None else np.asarray(position, dtype=float).reshape(3)
+        q = np.array([0.0, 0.0, 0.0, 1.0]) if quaternion is None else np.asarray(quaternion, dtype=float).reshape(4)
+        self._p = p.copy()
+        self._q = q / np.linalg.norm(q)
+
+    def translation(self):
+        return self._p.copy()
+
+    def quat(self):
+        return self._q.copy()
+
+    def coeffs(self):
+        return np.concatenate((self._p, self._q))            # manif order: translation, then quaternion
+
+    def rotation(self):
+        return layout.quat_to_rot(self._q)
+
+    def transform(self):
+        return layout.rows_to_se3(np.concatenate((self._q, self._p)))
+
+    def __repr__(self):
+        return f"SE3(position={self._p}, quaternion={self._q})"
+
+
+class SE3Tangent:
+    """Twist in manif's order [v, omega] (the library's own order is [omega, v]: see se32manifse3)."""
+
+    def __init__(self, coeffs):
+        self._c = np.asarray(coeffs, dtype=float).reshape(6).copy()
+
+    def coeffs(self):
+        return self._c.copy()
+
+    def __mul__(self, s):
+        return SE3Tangent(self._c * float(s))
+
+    __rmul__ = __mul__
+
+    def __repr__(self):
+        return f"SE3Tangent({self._c})"

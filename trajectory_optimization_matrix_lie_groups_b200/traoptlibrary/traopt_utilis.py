@@ -2,13 +2,14 @@
 
 Only the helpers the tracking scripts call around the solver are provided: hat/vee/ad maps
 (:13-92), quaternion / Euler / matrix conversions through scipy (:159-316), `is_pos_def` (:320-329).
-The manif converters (:331-399) have no counterpart: the device state row is already the
-(unit quaternion, position) pair those converters produce (see ..layout).
+The manif converters (:331-399) keep their names and meaning on the light stand-in types of
+`manif_compat` (the device state row is already the (unit quaternion, position) pair they produce).
 """
 import numpy as np
 from scipy.spatial.transform import Rotation
 
 from .. import layout
+from .manif_compat import SE3, SE3Tangent
 
 
 def skew(w):
@@ -154,3 +155,41 @@ def is_pos_def(A):
         except np.linalg.LinAlgError:
             return False
     return False
+
+
+def SE32manifSE3(x):
+    """4x4 pose -> SE3(position, quaternion [x,y,z,w]); the matrix -> quaternion step re-projects onto SO(3)
+    exactly as the reference's does (:331-342)."""
+    quatpos = SE32quatpos(x).reshape(7)
+    q0, q1, q2, q3 = quatpos[:4]
+    return SE3(position=quatpos[4:], quaternion=np.array([q1, q2, q3, q0]))
+
+
+def manifSE32SE3(x):
+    """SE3 object -> 4x4 pose (:344-354)."""
+    return x.transform()
+
+
+def se32manifse3(x):
+    """Twist [omega, v] -> SE3Tangent in manif's [v, omega] order (:356-367)."""
+    x = np.asarray(x, dtype=float).reshape(6)
+    return SE3Tangent(np.concatenate((x[3:], x[:3])))
+
+
+def manifse32se3(x):
+    """SE3Tangent (or its [v, omega] coefficients) -> twist [omega, v] (:369-383)."""
+    if isinstance(x, SE3Tangent):
+        x = x.coeffs()
+    x = np.asarray(x, dtype=float).reshape(6)
+    return np.concatenate((x[3:], x[:3]))
+
+
+def Jmnf2J(J):
+    """Reorder a 6x6 manif Jacobian ([v, omega] blocks) to the library's [omega, v] order (:387-399)."""
+    J = np.asarray(J)
+    return np.block([[J[3:, 3:], J[3:, :3]], [J[:3, 3:], J[:3, :3]]])
+
+
+def parallel_SE32manifSE3(q_ref):
+    """(:401-406); the reference maps over a thread pool, the result is the same list."""
+    return [SE32manifSE3(q) for q in q_ref]
