@@ -85,8 +85,10 @@ template <int KIND> constexpr int bwd_smem_doubles() {
     return D::NX * (D::NX + 1) + D::NU * (D::NX - 3) + D::NX;
 }
 
-template <int KIND, bool MS>
-__global__ void __launch_bounds__(kBlock) k_backward(const Params prm, Work w, int it) {
+// LPW = problems (active lanes) per warp: 32, or 16 to double the number of independent recursions in flight
+// when the batch alone cannot fill the schedulers (each CTA is ONE warp of LPW threads)
+template <int KIND, bool MS, int LPW>
+__global__ void __launch_bounds__(LPW) k_backward(const Params prm, Work w, int it) {
     using D = Dims<KIND>;
     using LR = LinRec<KIND>;
     constexpr int NX = D::NX, NP = D::NP, NU = D::NU, NV = NX - NP, F = LR::LEN;
@@ -95,14 +97,14 @@ __global__ void __launch_bounds__(kBlock) k_backward(const Params prm, Work w, i
     constexpr int NYC = NX - 3;      // columns of Y kept in shared memory
     extern __shared__ double sm[];
     const int lane = threadIdx.x;
-    const int b = blockIdx.x * kBlock + lane;
+    const int b = blockIdx.x * LPW + lane;
     if (b >= prm.B || w.status[b] != TRAJOPT_RUNNING) return;
     const int N = prm.N;
     const size_t Bp = (size_t)prm.Bp;
     double* Vs = sm + lane;
-    double* Vn = sm + NT * kBlock + lane;
-    double* Ys = sm + 2 * NT * kBlock + lane;
-    double* Vxs = sm + (2 * NT + NU * NYC) * kBlock + lane;
+    double* Vn = sm + NT * LPW + lane;
+    double* Ys = sm + 2 * NT * LPW + lane;
+    double* Vxs = sm + (2 * NT + NU * NYC) * LPW + lane;
     const double* __restrict__ lin = w.lin;
 
     // ---- cost / defect of the current trajectory ----------------------------------------
@@ -135,7 +137,7 @@ __global__ void __launch_bounds__(kBlock) k_backward(const Params prm, Work w, i
     {
         const double* rec = lin + lsoa(N, 0, F, N + 1, b);
 #pragma unroll
-        for (int j = 0; j < NX; ++j) Vxs[j * kBlock] = rec[(size_t)(LR::LX_OFF + j) * kRecStride];
+        for (int j = 0; j < NX; ++j) Vxs[j * LPW] = rec[(size_t)(LR::LX_OFF + j) * kRecStride];
 #pragma unroll
         for (int r = 0; r < NX; ++r)
 #pragma unroll
@@ -144,13 +146,13 @@ __global__ void __launch_bounds__(kBlock) k_backward(const Params prm, Work w, i
                 if (c < NP) v = rec[(size_t)(LR::LXX_OFF + tri_idx(NP, r, c)) * kRecStride];
                 else if (r >= NP) v = 2.0 * prm.P2[(r - NP) * NV + (c - NP)];
                 else v = 0.0;
-                Vs[tri_idx(NX, r, c) * kBlock] = v;
+                Vs[tri_idx(NX, r, c) * LPW] = v;
             }
     }
     double pad[NX];                      // SS: adjoint variable p (:2339)
     if constexpr (!MS) {
 #pragma unroll
-        for (int j = 0; j < NX; ++j) pad[j] = Vxs[j * kBlock];
+        for (int j = 0; j < NX; ++j) pad[j] = Vxs[j * LPW];
     }
 
     double mu = w.mu[b], delta = w.delta[b];
@@ -163,8 +165,8 @@ __global__ void __launch_bounds__(kBlock) k_backward(const Params prm, Work w, i
         if (i > 0) {   // pull the next record towards L2 while this stage computes
             const char* nxt = (const char*)(lin + lsoa(i - 1, 0, F, N + 1, b - lane));
 #pragma unroll
-            for (int t = 0; t < (F * 2 + kBlock - 1) / kBlock; ++t) {
-                const int line = t * kBlock + lane;
+            for (int t = 0; t < (F * 2 + LPW - 1) / LPW; ++t) {
+                const int line = t * LPW + lane;
                 if (line < F * 2) {
                     const char* p = nxt + (size_t)line * 128;
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
@@ -175,7 +177,7 @@ __global__ void __launch_bounds__(kBlock) k_backward(const Params prm, Work w, i
         // (1) v = V_x + V_xx d
         double v[NX];
 #pragma unroll
-        for (int r = 0; r < NX; ++r) v[r] = Vxs[r * kBlock];
+        for (int r = 0; r < NX; ++r) v[r] = Vxs[r * LPW];
         if constexpr (MS) {
             double d[NX];
 #pragma unroll
@@ -184,7 +186,7 @@ __global__ void __launch_bounds__(kBlock) k_backward(const Params prm, Work w, i
             for (int r = 0; r < NX; ++r)
 #pragma unroll
                 for (int c = r; c < NX; ++c) {
-                    const double t = Vs[tri_idx(NX, r, c) * kBlock];
+                    const double t = Vs[tri_idx(NX, r, c) * LPW];
                     v[r] = fma(t, d[c], v[r]);
                     if (c != r) v[c] = fma(t, d[r], v[c]);
                 }
@@ -251,7 +253,7 @@ __global__ void __launch_bounds__(kBlock) k_backward(const Params prm, Work w, i
                 });
 #pragma unroll
                 for (int j = 0; j < 3; ++j) {
-                    Vxs[(CB * 3 + j) * kBlock] = q[j];
+                    Vxs[(CB * 3 + j) * LPW] = q[j];
                     pn[CB * 3 + j] = qp[j];
                 }
             });
@@ -269,7 +271,7 @@ __global__ void __launch_bounds__(kBlock) k_backward(const Params prm, Work w, i
             for (int r = 0; r < NV; ++r) {
                 double vr[NV];
 #pragma unroll
-                for (int k = 0; k < NV; ++k) vr[k] = Vs[sym_idx(NX, NP + r, NP + k) * kBlock];
+                for (int k = 0; k < NV; ++k) vr[k] = Vs[sym_idx(NX, NP + r, NP + k) * LPW];
 #pragma unroll
                 for (int a = 0; a < NU; ++a) {
                     double s = 0.0;
@@ -384,7 +386,7 @@ __global__ void __launch_bounds__(kBlock) k_backward(const Params prm, Work w, i
                     for (int r = 0; r < NX; ++r)
 #pragma unroll
                         for (int ii = 0; ii < 3; ++ii) {
-                            const double t = Vs[sym_idx(NX, r, KB * 3 + ii) * kBlock];
+                            const double t = Vs[sym_idx(NX, r, KB * 3 + ii) * LPW];
 #pragma unroll
                             for (int j = 0; j < 3; ++j)
                                 if (blk_nz(kind, ii, j)) X[r][j] = fma(t, m[3 * ii + j], X[r][j]);
@@ -436,10 +438,10 @@ __global__ void __launch_bounds__(kBlock) k_backward(const Params prm, Work w, i
 #pragma unroll
                 for (int a = 0; a < NU; ++a) w.Kfb[soa(i, a * NX + CB * 3 + j, NU * NX, (int)Bp, b)] = -kk[a];
                 // V_x(i)[c] = Q_x[c] - Y[:,c]^T y
-                double s = Vxs[(CB * 3 + j) * kBlock];
+                double s = Vxs[(CB * 3 + j) * LPW];
 #pragma unroll
                 for (int a = 0; a < NU; ++a) s = fma(-Qux[a][j], y[a], s);
-                Vxs[(CB * 3 + j) * kBlock] = s;
+                Vxs[(CB * 3 + j) * LPW] = s;
             }
             // V_xx(i)[RB block, CB block] = l_xx + A[:, RB]^T X - Y[:, RB]^T Y[:, CB],  RB <= CB
             sfor<0, CB + 1>([&](auto rbc) {
@@ -480,7 +482,7 @@ __global__ void __launch_bounds__(kBlock) k_backward(const Params prm, Work w, i
 #pragma unroll
                     for (int ii = 0; ii < 3; ++ii) {
                         if constexpr (RB == CB) yr[ii] = Qux[a][ii];
-                        else yr[ii] = Ys[(a * NYC + RB * 3 + ii) * kBlock];
+                        else yr[ii] = Ys[(a * NYC + RB * 3 + ii) * LPW];
                     }
 #pragma unroll
                     for (int ii = 0; ii < 3; ++ii)
@@ -492,13 +494,13 @@ __global__ void __launch_bounds__(kBlock) k_backward(const Params prm, Work w, i
                 for (int ii = 0; ii < 3; ++ii)
 #pragma unroll
                     for (int j = 0; j < 3; ++j)
-                        if (RB < CB || ii <= j) Vn[tri_idx(NX, RB * 3 + ii, CB * 3 + j) * kBlock] = acc[ii][j];
+                        if (RB < CB || ii <= j) Vn[tri_idx(NX, RB * 3 + ii, CB * 3 + j) * LPW] = acc[ii][j];
             });
             if constexpr (CB * 3 < NYC) {
 #pragma unroll
                 for (int a = 0; a < NU; ++a)
 #pragma unroll
-                    for (int j = 0; j < 3; ++j) Ys[(a * NYC + CB * 3 + j) * kBlock] = Qux[a][j];
+                    for (int j = 0; j < 3; ++j) Ys[(a * NYC + CB * 3 + j) * LPW] = Qux[a][j];
             }
         });
         { double* t = Vs; Vs = Vn; Vn = t; }

@@ -135,10 +135,14 @@ int run_linearize(trajopt_handle* h, cudaStream_t s) {
 }
 
 // TRAJOPT_BACKWARD=1 selects the one-warp-per-group sweep for the 12-dimensional families too (A/B measurements)
-inline bool use_one_warp_sweep() {
-    static const bool v = [] { const char* e = getenv("TRAJOPT_BACKWARD"); return e && e[0] == '1'; }();
+// TRAJOPT_BACKWARD: 0 (default) two-warp CTA per 32 problems; 1 one warp per 32 problems (A/B measurements).
+// (16 problems per warp, i.e. twice the warps, was measured too: 16.2 ms per sweep against 12.2 — more warps per
+// scheduler streaming this straight-line code only fight over instruction fetch.)
+inline int backward_variant() {
+    static const int v = [] { const char* e = getenv("TRAJOPT_BACKWARD"); return e ? atoi(e) : 0; }();
     return v;
 }
+inline bool use_one_warp_sweep() { return backward_variant() != 0; }
 
 template <int KIND, bool MS>
 int run_backward(trajopt_handle* h, cudaStream_t s, int it) {
@@ -152,8 +156,8 @@ int run_backward(trajopt_handle* h, cudaStream_t s, int it) {
         }
     }
     constexpr size_t smem = (size_t)bwd_smem_doubles<KIND>() * kBlock * sizeof(double);
-    CUDA_OK(cudaFuncSetAttribute(k_backward<KIND, MS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    LAUNCH((k_backward<KIND, MS>), h->Bp / kBlock, kBlock, smem, s, h->prm, h->w, it);
+    CUDA_OK(cudaFuncSetAttribute(k_backward<KIND, MS, kBlock>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LAUNCH((k_backward<KIND, MS, kBlock>), h->Bp / kBlock, kBlock, smem, s, h->prm, h->w, it);
     return 0;
 }
 
