@@ -164,6 +164,10 @@ int64_t trajopt_launch_count(int reset);
  * out[0]=linearise, out[1]=backward, out[2]=forward, out[3]=other; and their launch counts in cnt[4] */
 int trajopt_phase_times(trajopt_handle* h, double* out_ms, int64_t* cnt, int reset);
 int trajopt_set_profiling(trajopt_handle* h, int enable);
+/* Compaction of the running problems into the leading slots during a solve (changes no result, only which CTAs
+ * stay busy): active once the (padded) batch is >= min_batch and running * ratio <= slots in use.  Defaults 1024, 4;
+ * min_batch < 0 disables it. */
+int trajopt_set_compaction(trajopt_handle* h, int min_batch, int ratio);
 
 #ifdef __cplusplus
 }

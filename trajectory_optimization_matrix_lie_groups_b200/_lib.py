@@ -85,6 +85,7 @@ SYMBOLS = {
     "trajopt_launch_count": (C.c_int64, [_I]),
     "trajopt_phase_times": (_I, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64), _I]),
     "trajopt_set_profiling": (_I, [_P, _I]),
+    "trajopt_set_compaction": (_I, [_P, _I, _I]),
 }
 
 

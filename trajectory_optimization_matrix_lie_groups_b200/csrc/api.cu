@@ -89,6 +89,7 @@ int trajopt_create(int kind, int method, int N, int B, int device, trajopt_handl
     A_(w.iters, Bp); A_(w.status, Bp); A_(w.ls_state, Bp);
     A_(w.x0, (size_t)h->NS * Bp);
     A_(w.counters, 4);
+    A_(w.orig, Bp);
     A_(h->d_dweight, Bp);
     if (method == TRAJOPT_AL_MS) {
         A_(w.lam, Np1 * 2 * h->NU * Bp); A_(w.imu, Np1 * 2 * h->NU * Bp);
@@ -114,6 +115,8 @@ int trajopt_destroy(trajopt_handle* h) {
     for (void* p : h->hist_allocs) if (p) cudaFree(p);
     void* stage[] = {h->s_x0, h->s_us0, h->s_xs, h->s_us, h->s_J, h->s_grad, h->s_def, h->s_iters, h->s_status};
     for (void* p : stage) if (p) cudaFree(p);
+    if (h->d_perm) cudaFree(h->d_perm);
+    if (h->d_scratch) cudaFree(h->d_scratch);
     if (h->h_counters) cudaFreeHost(h->h_counters);
     if (h->ev[0]) cudaEventDestroy(h->ev[0]);
     if (h->ev[1]) cudaEventDestroy(h->ev[1]);
@@ -250,14 +253,14 @@ int trajopt_export(trajopt_handle* h, double* d_xs, double* d_us, double* d_J, i
     DeviceGuard guard(h->device);
     cudaStream_t s = (cudaStream_t)stream;
     const Work& w = h->w;
-    const int bg = blocks_for(h->B, 128);
-    if (d_xs) LAUNCH(k_export_traj, dim3(bg, h->N + 1), 128, 0, s, h->B, h->Bp, h->NS, w.X[0], w.X[1], w.sel, d_xs, h->N + 1);
-    if (d_us) LAUNCH(k_export_traj, dim3(bg, h->N), 128, 0, s, h->B, h->Bp, h->NU, w.U[0], w.U[1], w.sel, d_us, h->N);
-    if (d_J) LAUNCH(k_export_rows<double>, dim3(bg, 1), 128, 0, s, h->B, h->Bp, 1, w.J, d_J);
-    if (d_grad) LAUNCH(k_export_rows<double>, dim3(bg, 1), 128, 0, s, h->B, h->Bp, 1, w.grad, d_grad);
-    if (d_defect) LAUNCH(k_export_rows<double>, dim3(bg, 1), 128, 0, s, h->B, h->Bp, 1, w.dnorm, d_defect);
-    if (d_iters) LAUNCH(k_export_rows<int>, dim3(bg, 1), 128, 0, s, h->B, h->Bp, 1, w.iters, (int*)d_iters);
-    if (d_status) LAUNCH(k_export_rows<int>, dim3(bg, 1), 128, 0, s, h->B, h->Bp, 1, w.status, (int*)d_status);
+    const int bg = blocks_for(h->Bp, 128);
+    if (d_xs) LAUNCH(k_export_traj, dim3(bg, h->N + 1), 128, 0, s, h->B, h->Bp, h->NS, w.X[0], w.X[1], w.sel, (const int*)h->w.orig, d_xs, h->N + 1);
+    if (d_us) LAUNCH(k_export_traj, dim3(bg, h->N), 128, 0, s, h->B, h->Bp, h->NU, w.U[0], w.U[1], w.sel, (const int*)h->w.orig, d_us, h->N);
+    if (d_J) LAUNCH(k_export_rows<double>, dim3(bg, 1), 128, 0, s, h->B, h->Bp, 1, w.J, (const int*)h->w.orig, d_J);
+    if (d_grad) LAUNCH(k_export_rows<double>, dim3(bg, 1), 128, 0, s, h->B, h->Bp, 1, w.grad, (const int*)h->w.orig, d_grad);
+    if (d_defect) LAUNCH(k_export_rows<double>, dim3(bg, 1), 128, 0, s, h->B, h->Bp, 1, w.dnorm, (const int*)h->w.orig, d_defect);
+    if (d_iters) LAUNCH(k_export_rows<int>, dim3(bg, 1), 128, 0, s, h->B, h->Bp, 1, w.iters, (const int*)h->w.orig, (int*)d_iters);
+    if (d_status) LAUNCH(k_export_rows<int>, dim3(bg, 1), 128, 0, s, h->B, h->Bp, 1, w.status, (const int*)h->w.orig, (int*)d_status);
     return 0;
 }
 
@@ -268,12 +271,12 @@ int trajopt_export_hist(trajopt_handle* h, double* d_J_hist, double* d_grad_hist
     DeviceGuard guard(h->device);
     cudaStream_t s = (cudaStream_t)stream;
     const Work& w = h->w;
-    const int bg = blocks_for(h->B, 128), mi = h->prm.max_iters;
+    const int bg = blocks_for(h->Bp, 128), mi = h->prm.max_iters;
     if (mi == 0) return 0;
-    if (d_J_hist) LAUNCH(k_export_rows<double>, dim3(bg, mi), 128, 0, s, h->B, h->Bp, mi, w.Jhist, d_J_hist);
-    if (d_grad_hist) LAUNCH(k_export_rows<double>, dim3(bg, mi + 1), 128, 0, s, h->B, h->Bp, mi + 1, w.gradhist, d_grad_hist);
-    if (d_defect_hist) LAUNCH(k_export_rows<double>, dim3(bg, mi + 1), 128, 0, s, h->B, h->Bp, mi + 1, w.defhist, d_defect_hist);
-    if (d_alpha_hist) LAUNCH(k_export_rows<int>, dim3(bg, mi), 128, 0, s, h->B, h->Bp, mi, w.alphahist, (int*)d_alpha_hist);
+    if (d_J_hist) LAUNCH(k_export_rows<double>, dim3(bg, mi), 128, 0, s, h->B, h->Bp, mi, w.Jhist, (const int*)h->w.orig, d_J_hist);
+    if (d_grad_hist) LAUNCH(k_export_rows<double>, dim3(bg, mi + 1), 128, 0, s, h->B, h->Bp, mi + 1, w.gradhist, (const int*)h->w.orig, d_grad_hist);
+    if (d_defect_hist) LAUNCH(k_export_rows<double>, dim3(bg, mi + 1), 128, 0, s, h->B, h->Bp, mi + 1, w.defhist, (const int*)h->w.orig, d_defect_hist);
+    if (d_alpha_hist) LAUNCH(k_export_rows<int>, dim3(bg, mi), 128, 0, s, h->B, h->Bp, mi, w.alphahist, (const int*)h->w.orig, (int*)d_alpha_hist);
     return 0;
 }
 
@@ -282,9 +285,9 @@ int trajopt_export_reg(trajopt_handle* h, double* d_mu, double* d_delta, void* s
     if (!h->begun) return fail(TRAJOPT_E_STATE, "trajopt_export_reg: nothing solved yet");
     DeviceGuard guard(h->device);
     cudaStream_t s = (cudaStream_t)stream;
-    const int bg = blocks_for(h->B, 128);
-    if (d_mu) LAUNCH(k_export_rows<double>, dim3(bg, 1), 128, 0, s, h->B, h->Bp, 1, h->w.mu, d_mu);
-    if (d_delta) LAUNCH(k_export_rows<double>, dim3(bg, 1), 128, 0, s, h->B, h->Bp, 1, h->w.delta, d_delta);
+    const int bg = blocks_for(h->Bp, 128);
+    if (d_mu) LAUNCH(k_export_rows<double>, dim3(bg, 1), 128, 0, s, h->B, h->Bp, 1, h->w.mu, (const int*)h->w.orig, d_mu);
+    if (d_delta) LAUNCH(k_export_rows<double>, dim3(bg, 1), 128, 0, s, h->B, h->Bp, 1, h->w.delta, (const int*)h->w.orig, d_delta);
     return 0;
 }
 
@@ -296,12 +299,12 @@ int trajopt_export_al(trajopt_handle* h, double* d_lmbd, double* d_imu, double* 
     DeviceGuard guard(h->device);
     cudaStream_t s = (cudaStream_t)stream;
     const Work& w = h->w;
-    const int bg = blocks_for(h->B, 128);
-    if (d_lmbd) LAUNCH(k_export_traj, dim3(bg, h->N + 1), 128, 0, s, h->B, h->Bp, 2 * h->NU, w.lam, w.lam, (const int*)nullptr, d_lmbd, h->N + 1);
-    if (d_imu) LAUNCH(k_export_traj, dim3(bg, h->N + 1), 128, 0, s, h->B, h->Bp, 2 * h->NU, w.imu, w.imu, (const int*)nullptr, d_imu, h->N + 1);
-    if (d_mu) LAUNCH(k_export_rows<double>, dim3(bg, 1), 128, 0, s, h->B, h->Bp, 1, w.al_mu, d_mu);
-    if (d_violation) LAUNCH(k_export_rows<double>, dim3(bg, 1), 128, 0, s, h->B, h->Bp, 1, w.al_viol, d_violation);
-    if (d_outer_iters) LAUNCH(k_export_rows<int>, dim3(bg, 1), 128, 0, s, h->B, h->Bp, 1, w.al_outer, (int*)d_outer_iters);
+    const int bg = blocks_for(h->Bp, 128);
+    if (d_lmbd) LAUNCH(k_export_traj, dim3(bg, h->N + 1), 128, 0, s, h->B, h->Bp, 2 * h->NU, w.lam, w.lam, (const int*)nullptr, (const int*)h->w.orig, d_lmbd, h->N + 1);
+    if (d_imu) LAUNCH(k_export_traj, dim3(bg, h->N + 1), 128, 0, s, h->B, h->Bp, 2 * h->NU, w.imu, w.imu, (const int*)nullptr, (const int*)h->w.orig, d_imu, h->N + 1);
+    if (d_mu) LAUNCH(k_export_rows<double>, dim3(bg, 1), 128, 0, s, h->B, h->Bp, 1, w.al_mu, (const int*)h->w.orig, d_mu);
+    if (d_violation) LAUNCH(k_export_rows<double>, dim3(bg, 1), 128, 0, s, h->B, h->Bp, 1, w.al_viol, (const int*)h->w.orig, d_violation);
+    if (d_outer_iters) LAUNCH(k_export_rows<int>, dim3(bg, 1), 128, 0, s, h->B, h->Bp, 1, w.al_outer, (const int*)h->w.orig, (int*)d_outer_iters);
     return 0;
 }
 
@@ -371,9 +374,9 @@ int trajopt_debug_gains(trajopt_handle* h, double* d_k, double* d_K, void* strea
     if (!h->begun) return fail(TRAJOPT_E_STATE, "trajopt_debug_gains: call trajopt_begin first");
     DeviceGuard guard(h->device);
     cudaStream_t s = (cudaStream_t)stream;
-    const int bg = blocks_for(h->B, 128);
-    if (d_k) LAUNCH(k_export_traj, dim3(bg, h->N), 128, 0, s, h->B, h->Bp, h->NU, h->w.kff, h->w.kff, (const int*)nullptr, d_k, h->N);
-    if (d_K) LAUNCH(k_export_traj, dim3(bg, h->N), 128, 0, s, h->B, h->Bp, h->NU * h->NX, h->w.Kfb, h->w.Kfb, (const int*)nullptr, d_K, h->N);
+    const int bg = blocks_for(h->Bp, 128);
+    if (d_k) LAUNCH(k_export_traj, dim3(bg, h->N), 128, 0, s, h->B, h->Bp, h->NU, h->w.kff, h->w.kff, (const int*)nullptr, (const int*)h->w.orig, d_k, h->N);
+    if (d_K) LAUNCH(k_export_traj, dim3(bg, h->N), 128, 0, s, h->B, h->Bp, h->NU * h->NX, h->w.Kfb, h->w.Kfb, (const int*)nullptr, (const int*)h->w.orig, d_K, h->N);
     return 0;
 }
 
@@ -458,6 +461,14 @@ int trajopt_phase_times(trajopt_handle* h, double* out_ms, int64_t* cnt, int res
         if (cnt) cnt[i] = h->phase_cnt[i];
         if (reset) { h->phase_ms[i] = 0.0; h->phase_cnt[i] = 0; }
     }
+    return 0;
+}
+
+int trajopt_set_compaction(trajopt_handle* h, int min_batch, int ratio) {
+    if (!h) return fail(TRAJOPT_E_INVALID, "trajopt_set_compaction: NULL handle");
+    if (ratio < 1) return fail(TRAJOPT_E_INVALID, "trajopt_set_compaction: ratio must be >= 1");
+    h->compact_min_batch = min_batch;
+    h->compact_ratio = ratio;
     return 0;
 }
 

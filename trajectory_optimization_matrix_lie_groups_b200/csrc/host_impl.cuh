@@ -39,6 +39,11 @@ struct trajopt_handle {
     int al_outer = 0;        // AL outer iterations completed
     bool al_finished = false;
     int hist_cap = -1, cand_rows = -1;
+    // compaction: leading slots that may hold running problems; thresholds (see maybe_compact)
+    int front = 0, compact_min_batch = 1024, compact_ratio = 4;
+    int* d_perm = nullptr;
+    void* d_scratch = nullptr;
+    size_t scratch_bytes = 0;
     std::vector<void*> allocs;
     void* hist_allocs[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     double* d_ref = nullptr;
@@ -237,6 +242,74 @@ int inner_iteration(trajopt_handle* h, cudaStream_t s) {
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------
+// Compaction.  Every launch of the sweep kernels costs the same whether 16384 or 300 problems are still
+// running (one sequential recursion per problem), but a CTA is only released when all of its 32 problems
+// have finished — and the slow problems of a batch are usually spread over every warp.  Once the running
+// problems are few, they are moved (stable partition) to the leading slots: the other CTAs exit at once and
+// leave their SMs to whatever else is in flight on the device (the next batch of a PipelinedSolver).
+// A problem's result does not depend on its slot (tests/test_gpu_fullsize.py), so this changes no number.
+// Everything that is per problem and survives an iteration boundary moves; linearisation records, gains and
+// G_i are rebuilt by the next iteration anyway.  `orig` remembers the caller's index for the exports.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+int permute_array(trajopt_handle* h, cudaStream_t s, T* data, size_t rows, int front) {
+    if (!data || rows == 0) return 0;
+    const size_t need = rows * (size_t)front * sizeof(T);
+    if (need > h->scratch_bytes) {
+        if (h->d_scratch) cudaFree(h->d_scratch);
+        h->d_scratch = nullptr;
+        h->scratch_bytes = 0;
+        CUDA_OK(cudaMalloc(&h->d_scratch, need));
+        h->scratch_bytes = need;
+    }
+    dim3 grid(blocks_for(front, 128), (unsigned)std::min<size_t>(rows, 4096));
+    LAUNCH((k_permute_gather<T>), grid, 128, 0, s, (int)rows, h->Bp, front, (const T*)data, (const int*)h->d_perm, (T*)h->d_scratch);
+    LAUNCH((k_permute_scatter<T>), grid, 128, 0, s, (int)rows, h->Bp, front, data, (const T*)h->d_scratch);
+    return 0;
+}
+
+inline int maybe_compact(trajopt_handle* h, cudaStream_t s, int act) {
+    if (h->compact_min_batch < 0 || h->Bp < h->compact_min_batch || act <= 0) return 0;
+    const int front = h->front;
+    if ((long long)act * h->compact_ratio > front || act >= front) return 0;
+    PhaseTimer t(h, s, PH_OTHER);
+    std::vector<int> st((size_t)front), src_of((size_t)front);
+    CUDA_OK(cudaMemcpyAsync(st.data(), h->w.status, (size_t)front * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CUDA_OK(cudaStreamSynchronize(s));
+    int n = 0, last_running = -1;
+    for (int b = 0; b < front; ++b)
+        if ((st[b] & 15) == TRAJOPT_RUNNING) { src_of[n++] = b; last_running = b; }
+    const int new_front = (n + 31) / 32 * 32;
+    if (last_running < new_front) {      // already packed: just shrink the front
+        h->front = std::max(new_front, 32);
+        return 0;
+    }
+    for (int b = 0; b < front; ++b)
+        if ((st[b] & 15) != TRAJOPT_RUNNING) src_of[n++] = b;
+    if (!h->d_perm) CUDA_OK(cudaMalloc((void**)&h->d_perm, (size_t)h->Bp * sizeof(int)));
+    CUDA_OK(cudaMemcpyAsync(h->d_perm, src_of.data(), (size_t)front * sizeof(int), cudaMemcpyHostToDevice, s));
+    Work& w = h->w;
+    const size_t Np1 = (size_t)h->N + 1, N = (size_t)h->N, mi = (size_t)std::max(h->prm.max_iters, 1);
+    int rc = 0;
+#define P_(ptr, rows) if (!rc) rc = permute_array(h, s, (ptr), (size_t)(rows), front)
+    P_(w.X[0], Np1 * h->NS); P_(w.X[1], Np1 * h->NS); P_(w.U[0], N * h->NU); P_(w.U[1], N * h->NU);
+    P_(w.x0, h->NS); P_(w.sel, 1); P_(w.orig, 1);
+    P_(w.J, 1); P_(w.grad, 1); P_(w.dnorm, 1); P_(w.mu, 1); P_(w.delta, 1);
+    P_(w.iters, 1); P_(w.status, 1); P_(w.ls_state, 1);
+    P_(w.Jhist, mi); P_(w.gradhist, mi + 1); P_(w.defhist, mi + 1); P_(w.alphahist, mi);
+    P_(h->d_dweight, 1);
+    if (h->method == TRAJOPT_AL_MS) {
+        P_(w.lam, Np1 * 2 * h->NU); P_(w.imu, Np1 * 2 * h->NU);
+        P_(w.al_mu, 1); P_(w.al_outer, 1); P_(w.al_viol, 1); P_(w.al_done, 1);
+    }
+#undef P_
+    if (rc) return rc;
+    CUDA_OK(cudaStreamSynchronize(s));    // src_of (host) was read by an async copy
+    h->front = std::max(new_front, 32);
+    return 0;
+}
+
 // run the inner loop for up to n_iters iterations; *active = problems still running
 template <int KIND>
 int run_inner(trajopt_handle* h, cudaStream_t s, int n_iters, int* active) {
@@ -247,6 +320,7 @@ int run_inner(trajopt_handle* h, cudaStream_t s, int n_iters, int* active) {
         if ((rc = inner_iteration<KIND>(h, s))) return rc;
         if ((rc = count_running(h, s, &act))) return rc;
         if (act == 0) break;
+        if ((rc = maybe_compact(h, s, act))) return rc;
     }
     if (act < 0 && (rc = count_running(h, s, &act))) return rc;
     if (act == 0 || h->it >= last) h->inner_done = true;
@@ -273,6 +347,7 @@ int start_inner(trajopt_handle* h, cudaStream_t s, bool al_restart) {
     }
     h->it = 0;
     h->inner_done = false;
+    h->front = h->Bp;
     return 0;
 }
 
@@ -280,6 +355,14 @@ template <int KIND>
 int begin_impl(trajopt_handle* h, const double* d_x0, const double* d_us_init, int us_mode, cudaStream_t s) {
     h->w.us_init = d_us_init;
     h->w.us_mode = d_us_init ? us_mode : 0;
+    LAUNCH(k_identity, blocks_for(h->Bp, 128), 128, 0, s, h->Bp, h->w.orig);
+    {   // histories: entries past a problem's last iteration read as zero
+        const size_t Bp = (size_t)h->Bp, cap = (size_t)std::max(h->prm.max_iters, 1), cap1 = (size_t)h->prm.max_iters + 1;
+        CUDA_OK(cudaMemsetAsync(h->w.Jhist, 0, cap * Bp * sizeof(double), s));
+        CUDA_OK(cudaMemsetAsync(h->w.gradhist, 0, cap1 * Bp * sizeof(double), s));
+        CUDA_OK(cudaMemsetAsync(h->w.defhist, 0, cap1 * Bp * sizeof(double), s));
+        CUDA_OK(cudaMemsetAsync(h->w.alphahist, 0, cap * Bp * sizeof(int), s));
+    }
     LAUNCH((k_load_x0<KIND>), blocks_for(h->Bp, 128), 128, 0, s, h->prm, h->w, d_x0);
     if (h->method == TRAJOPT_AL_MS) {
         dim3 grid(blocks_for(h->Bp, 128), h->N + 1);
@@ -333,7 +416,7 @@ int debug_linearize_impl(trajopt_handle* h, double* Fx, double* Fu, double* dd, 
     if (h->method == TRAJOPT_SS) rc = run_linearize<KIND, false>(h, s);
     else rc = run_linearize<KIND, true>(h, s);
     if (rc) return rc;
-    dim3 grid(blocks_for(h->B, 128), h->N + 1);
+    dim3 grid(blocks_for(h->Bp, 128), h->N + 1);
     LAUNCH((k_export_lin<KIND>), grid, 128, 0, s, h->prm, h->w, Fx, Fu, dd, L, Lx, Lxx, Lu);
     return 0;
 }

@@ -49,6 +49,7 @@ struct Work {
     double* al_viol;     // [Bp]
     int* al_done;        // [Bp]
     int* counters;       // [0] running problems, [1] pending line searches, [2] AL problems not converged
+    int* orig;           // [Bp] slot -> problem index of the caller (identity until a compaction moves problems)
 };
 
 constexpr int kBlock = 32;
@@ -180,7 +181,7 @@ __device__ __forceinline__ double us_init_value(const Work& w, const Params& prm
     constexpr int NU = Dims<KIND>::NU;
     if (w.us_mode == 0 || w.us_init == nullptr) return 0.0;
     if (w.us_mode == 1) return w.us_init[(size_t)stage * NU + j];
-    return w.us_init[((size_t)b * prm.N + stage) * NU + j];
+    return w.us_init[((size_t)w.orig[b] * prm.N + stage) * NU + j];
 }
 
 // x0 arrives problem-major [B][NS]; keep a normalised SoA copy

@@ -598,20 +598,46 @@ __global__ void k_al_init(const Params prm, Work w, double mu0) {
 // Layout exports: SoA [stage][field][Bp] -> problem-major
 // ------------------------------------------------------------------------------------------
 // out[b][stage][f] = src_sel[b][stage][f][b]   (grid.y = stage)
-static __global__ void k_export_traj(int B, int Bp, int F, const double* s0, const double* s1, const int* sel, double* out, int nstage) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+static __global__ void k_export_traj(int B, int Bp, int F, const double* s0, const double* s1, const int* sel,
+                                     const int* __restrict__ orig, double* out, int nstage) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;   // slot
     const int stage = blockIdx.y;
-    if (b >= B) return;
+    if (b >= Bp) return;
+    const int o = orig[b];                                  // the caller's problem index
+    if (o >= B) return;
     const double* src = (sel && sel[b]) ? s1 : s0;
-    for (int f = 0; f < F; ++f) out[((size_t)b * nstage + stage) * F + f] = src[((size_t)stage * F + f) * Bp + b];
+    for (int f = 0; f < F; ++f) out[((size_t)o * nstage + stage) * F + f] = src[((size_t)stage * F + f) * Bp + b];
 }
-// out[b][row] = src[row][b]
+// out[orig[b]][row] = src[row][b]
 template <typename T>
-__global__ void k_export_rows(int B, int Bp, int rows, const T* src, T* out) {
+__global__ void k_export_rows(int B, int Bp, int rows, const T* src, const int* __restrict__ orig, T* out) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     const int r = blockIdx.y;
-    if (b >= B) return;
-    out[(size_t)b * rows + r] = src[(size_t)r * Bp + b];
+    if (b >= Bp) return;
+    const int o = orig[b];
+    if (o >= B) return;
+    out[(size_t)o * rows + r] = src[(size_t)r * Bp + b];
+}
+
+// Compaction (see maybe_compact in host_impl.cuh): gather the leading `front` slots of a [rows][Bp] array into their
+// new order, in two steps through a scratch buffer:  scratch[r][n] = data[r][src_of[n]];  data[r][n] = scratch[r][n].
+template <typename T>
+__global__ void k_permute_gather(int rows, int Bp, int front, const T* __restrict__ data, const int* __restrict__ src_of,
+                                 T* __restrict__ scratch) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= front) return;
+    const int src = src_of[n];
+    for (int r = blockIdx.y; r < rows; r += gridDim.y) scratch[(size_t)r * front + n] = data[(size_t)r * Bp + src];
+}
+template <typename T>
+__global__ void k_permute_scatter(int rows, int Bp, int front, T* __restrict__ data, const T* __restrict__ scratch) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= front) return;
+    for (int r = blockIdx.y; r < rows; r += gridDim.y) data[(size_t)r * Bp + n] = scratch[(size_t)r * front + n];
+}
+static __global__ void k_identity(int n, int* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = i;
 }
 
 // dense linearisation for parity tests
@@ -623,11 +649,13 @@ __global__ void k_export_lin(const Params prm, Work w, double* Fx, double* Fu, d
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = blockIdx.y;
     const int Bp = prm.Bp, N = prm.N;
-    if (b >= prm.B) return;
+    if (b >= Bp) return;
+    const int o = w.orig[b];           // output row = the caller's problem index
+    if (o >= prm.B) return;
     const double* lin = w.lin;
-    if (L) L[(size_t)b * (N + 1) + i] = w.Lc[(size_t)i * Bp + b];
+    if (L) L[(size_t)o * (N + 1) + i] = w.Lc[(size_t)i * Bp + b];
     if (Lx)
-        for (int c = 0; c < NX; ++c) Lx[((size_t)b * (N + 1) + i) * NX + c] = lin[lsoa(i, LR::LX_OFF + c, F, N + 1, b)];
+        for (int c = 0; c < NX; ++c) Lx[((size_t)o * (N + 1) + i) * NX + c] = lin[lsoa(i, LR::LX_OFF + c, F, N + 1, b)];
     if (Lxx) {
         const double* W2 = (i == N) ? prm.P2 : prm.W2;
         for (int r = 0; r < NX; ++r)
@@ -635,7 +663,7 @@ __global__ void k_export_lin(const Params prm, Work w, double* Fx, double* Fu, d
                 double v = 0.0;
                 if (r < NP && c < NP) v = lin[lsoa(i, LR::LXX_OFF + sym_idx(NP, r, c), F, N + 1, b)];
                 else if (r >= NP && c >= NP) v = 2.0 * W2[(r - NP) * NV + (c - NP)];
-                Lxx[(((size_t)b * (N + 1) + i) * NX + r) * NX + c] = v;
+                Lxx[(((size_t)o * (N + 1) + i) * NX + r) * NX + c] = v;
             }
     }
     if (i == N) return;
@@ -646,18 +674,18 @@ __global__ void k_export_lin(const Params prm, Work w, double* Fx, double* Fu, d
         for (int r = 0; r < NX; ++r)
 #pragma unroll
             for (int c = 0; c < NX; ++c)
-                Fx[(((size_t)b * N + i) * NX + r) * NX + c] = AMat<KIND>::nz(r, c) ? A.get(r, c) : 0.0;
+                Fx[(((size_t)o * N + i) * NX + r) * NX + c] = AMat<KIND>::nz(r, c) ? A.get(r, c) : 0.0;
     }
     if (Fu) {
         const BvStage<KIND> Bv(prm, lin + lsoa(i, 0, F, N + 1, b), kRecStride);
         for (int r = 0; r < NX; ++r)
             for (int a = 0; a < NU; ++a)
-                Fu[(((size_t)b * N + i) * NX + r) * NU + a] = (r >= NP && bv_nz<KIND>(r - NP, a)) ? Bv.get(r - NP, a) : 0.0;
+                Fu[(((size_t)o * N + i) * NX + r) * NU + a] = (r >= NP && bv_nz<KIND>(r - NP, a)) ? Bv.get(r - NP, a) : 0.0;
     }
     if (dd)
-        for (int c = 0; c < NX; ++c) dd[((size_t)b * N + i) * NX + c] = lin[lsoa(i, LR::D_OFF + c, F, N + 1, b)];
+        for (int c = 0; c < NX; ++c) dd[((size_t)o * N + i) * NX + c] = lin[lsoa(i, LR::D_OFF + c, F, N + 1, b)];
     if (Lu)
-        for (int a = 0; a < NU; ++a) Lu[((size_t)b * N + i) * NU + a] = lin[lsoa(i, LR::LU_OFF + a, F, N + 1, b)];
+        for (int a = 0; a < NU; ++a) Lu[((size_t)o * N + i) * NU + a] = lin[lsoa(i, LR::LU_OFF + a, F, N + 1, b)];
 }
 
 }  // namespace trajopt

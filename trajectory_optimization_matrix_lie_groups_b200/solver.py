@@ -250,6 +250,10 @@ class BatchSolver:
                                       _ptr(out["l_xx"]), _ptr(out["l_u"]), _ptr(out["err"]), _stream(self.device)))
         return {k: v for k, v in out.items() if v is not None}
 
+    def set_compaction(self, min_batch=1024, ratio=4):
+        """Pack the running problems into the leading slots once running * ratio <= slots in use (min_batch < 0: never)."""
+        check(lib.trajopt_set_compaction(self._h, int(min_batch), int(ratio)))
+
     def set_profiling(self, on):
         check(lib.trajopt_set_profiling(self._h, int(bool(on))))
 
