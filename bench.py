@@ -228,6 +228,10 @@ def run_gpu_arm(args):
     x0_rows = wl.x0_rows[rank * B:rank * B + B]
     pipe = PipelinedSolver(lambda: wl.make_solver(B=B, device=dev, offset=rank * B)[0], depth=depth, device=dev)
     solver = pipe.solvers[0]
+    if args.compact:
+        mb, ratio = (int(v) for v in args.compact.split(","))
+        for sv in pipe.solvers:
+            sv.set_compaction(mb, ratio)
     x0_dev = torch.as_tensor(x0_rows, device=dev)
     x0_pin = torch.as_tensor(x0_rows).pin_memory()
     want_traj = not args.no_traj
@@ -409,6 +413,7 @@ def main():
     ap.add_argument("--no-traj", action="store_true", help="e2e leg returns only the per-problem summaries")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--inflight", type=int, default=2, help="batches in flight per GPU (1 = strictly one after the other)")
+    ap.add_argument("--compact", default="", help="'min_batch,ratio' for trajopt_set_compaction (default: the library's 1024,4; '-1,4' = off)")
     args = ap.parse_args()
     if args.batch is None:
         args.batch = {1: 1, 2: 1024, 3: 16384, 4: 2048, 5: 131072}[args.config]
