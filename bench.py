@@ -379,6 +379,16 @@ def run_gpu_arm(args):
                            "hbm_frac": bytes_step / step_s / 1e9 / hbm_peak, "hbm_peak_gbs": hbm_peak,
                            "hbm_peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback",
                            "algorithmic_gflop_per_step": flop_step / 1e9, "algorithmic_gb_per_step": bytes_step / 1e9},
+        "kernels": [
+            {"kernel": "k_linearize", "bound": "hbm", "ms_per_launch": lin_ms / max(lin_n, 1), "share_of_step": lin_ms / phase_total,
+             "achieved": workloads.LIN_RECORD_DOUBLES[wl.kind] * 8.0 * (wl.N + 1) * sweeps / (lin_ms * 1e-3) / 1e9, "peak": hbm_peak,
+             "unit": "GB/s", "frac": workloads.LIN_RECORD_DOUBLES[wl.kind] * 8.0 * (wl.N + 1) * sweeps / (lin_ms * 1e-3) / 1e9 / hbm_peak,
+             "note": "bytes = the records the kernel writes by design (the SURVEY byte model assumes none: linearisation recomputed in the sweep)"},
+            {"kernel": "k_forward_ms_full" if wl.method != "ss" else "k_forward", "bound": "latency (sequential Exp/Log chain); hbm secondary",
+             "ms_per_launch": fwd_ms / max(fwd_n, 1), "share_of_step": fwd_ms / phase_total,
+             "achieved": model["bytes_fwd"] * wl.N * rollouts / (fwd_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+             "frac": model["bytes_fwd"] * wl.N * rollouts / (fwd_ms * 1e-3) / 1e9 / hbm_peak},
+        ] if lin_ms > 0 and fwd_ms > 0 else [],
         "single_batch": {"ms": serial_ms, "solves_per_s": B / (serial_ms * 1e-3),
                          "note": "one batch alone on the GPU (nothing else in flight): step latency / serial throughput"},
         "phases_ms": {"linearize": lin_ms, "backward": bwd_ms, "forward": fwd_ms, "other": oth_ms,

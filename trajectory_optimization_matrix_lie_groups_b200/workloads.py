@@ -203,4 +203,8 @@ WORK_MODEL = {
     "se3": dict(flop_bwd=19140.0, flop_lin=3200.0, flop_fwd=2300.0, bytes_bwd=776.0, bytes_fwd=928.0),
     "drone": dict(flop_bwd=14872.0, flop_lin=3400.0, flop_fwd=2400.0, bytes_bwd=552.0, bytes_fwd=688.0),
     "so3": dict(flop_bwd=2730.0, flop_lin=600.0, flop_fwd=500.0, bytes_bwd=248.0, bytes_fwd=328.0),
+    "rigid": dict(flop_bwd=19140.0, flop_lin=3400.0, flop_fwd=2400.0, bytes_bwd=776.0, bytes_fwd=928.0),
+    "pendulum": dict(flop_bwd=2730.0, flop_lin=800.0, flop_fwd=600.0, bytes_bwd=248.0, bytes_fwd=328.0),
 }
+# doubles the linearisation kernel writes per stage-iteration as designed (record + G_i + stage cost + defect norm)
+LIN_RECORD_DOUBLES = {"se3": 114 + 13 + 2, "rigid": 117 + 13 + 2, "drone": 113 + 13 + 2, "so3": 54 + 7 + 2, "pendulum": 72 + 7 + 2}
