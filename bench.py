@@ -422,11 +422,14 @@ def main():
     ap.add_argument("--batch", type=int, default=None, help="problems per GPU")
     ap.add_argument("--no-traj", action="store_true", help="e2e leg returns only the per-problem summaries")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--inflight", type=int, default=2, help="batches in flight per GPU (1 = strictly one after the other)")
+    ap.add_argument("--inflight", type=int, default=0,
+                    help="batches in flight per GPU (1 = strictly one after the other; 0 = auto: 2, or 8 for batches <= 2048)")
     ap.add_argument("--compact", default="", help="'min_batch,ratio' for trajopt_set_compaction (default: the library's 1024,4; '-1,4' = off)")
     args = ap.parse_args()
     if args.batch is None:
         args.batch = {1: 1, 2: 1024, 3: 16384, 4: 2048, 5: 131072}[args.config]
+    if args.inflight <= 0:
+        args.inflight = 2 if args.batch > 2048 else 8
     if args.impl == "reference":
         return run_reference_arm(args)
     return run_gpu_arm(args)
