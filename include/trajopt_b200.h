@@ -101,6 +101,12 @@ int trajopt_set_params(trajopt_handle* h, const trajopt_params* p);
 /* h_q_ref [N+1][7] (SE3/drone) or [N+1][4] (SO3), h_xi_ref [N+1][6|3]; host pointers, shared by the batch */
 int trajopt_set_reference(trajopt_handle* h, const double* h_q_ref, const double* h_xi_ref);
 
+/* One reference per problem (the batch differs in references as well as in initial states): DEVICE pointers,
+ * problem-major d_q_ref [B][N+1][7|4], d_xi_ref [B][N+1][6|3].  Replaces the shared reference until the next
+ * trajopt_set_reference.  The multiple-shooting initial guess (traopt_controller.py:3123-3136) and the tracking cost
+ * (traopt_cost.py:614-616) of problem b then use reference b. */
+int trajopt_set_reference_batch(trajopt_handle* h, const double* d_q_ref, const double* d_xi_ref, void* stream);
+
 /* us_mode: 0 = zeros (d_us_init ignored), 1 = one [N][NU] path shared by the batch, 2 = [B][N][NU] */
 int trajopt_begin(trajopt_handle* h, const double* d_x0, const double* d_us_init, int us_mode, void* stream);
 /* run up to n_iters more iterations; *n_active_out (may be NULL) = problems still running afterwards */

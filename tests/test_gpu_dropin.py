@@ -151,3 +151,22 @@ def test_al_controller_runs_and_respects_bounds():
     assert seen[-1][1] and np.max(np.abs(us)) < 8.0 + 1e-2
     assert [s[2] for s in seen[:3]] == [1e-2, 1e-1, 1.0]      # penalty schedule mu0 = 1e-2, x10 per outer iteration
     assert len(seen) == 10                                     # oracle: 10 outer iterations for this problem
+
+
+def test_fit_batch_with_per_problem_references():
+    g, kind, dyn, cost, ctrl, x0, N = _mk("se3_n120", "ms")
+    import copy
+    B, Nh = 3, 40
+    from trajectory_optimization_matrix_lie_groups_b200.traoptlibrary import traopt_controller as tc, traopt_cost
+    q_full, xi_full = g["prob_q_ref"], g["prob_xi_ref"]
+    qb = np.stack([q_full[7 * b:7 * b + Nh + 1] for b in range(B)])
+    xb = np.stack([xi_full[7 * b:7 * b + Nh + 1] for b in range(B)])
+    cost_h = traopt_cost.SE3TrackingQuadraticGaussNewtonCost(g["prob_Q"], g["prob_R"], g["prob_P"], qb[0], xb[0])
+    ctrl_h = tc.iLQR_Tracking_SE3_MS(dyn, cost_h, Nh, qb[0], xb[0], rollout="nonlinear")
+    res = ctrl_h.fit_batch([x0] * B, n_iterations=60, tol_grad_norm=1e-10, q_ref_batch=qb, xi_ref_batch=xb)
+    assert np.all(res.converged)
+    for b in range(B):      # the same problem through the single-problem API with that reference
+        cost_b = traopt_cost.SE3TrackingQuadraticGaussNewtonCost(g["prob_Q"], g["prob_R"], g["prob_P"], qb[b], xb[b])
+        ctrl_b = tc.iLQR_Tracking_SE3_MS(dyn, cost_b, Nh, qb[b], xb[b], rollout="nonlinear")
+        xs, us, *_ = ctrl_b.fit(x0, np.zeros((Nh, 6)), n_iterations=60, tol_grad_norm=1e-10)
+        assert np.max(np.abs(us - res.us[b])) < 1e-9

@@ -97,6 +97,7 @@ int trajopt_create(int kind, int method, int N, int B, int device, trajopt_handl
     }
 #undef A_
     w.ref = h->d_ref;
+    w.ref_batch = nullptr;
     if (!rc && cudaMallocHost((void**)&h->h_counters, 4 * sizeof(int)) != cudaSuccess) rc = fail(TRAJOPT_E_CUDA, "cudaMallocHost failed");
     if (!rc && (cudaEventCreate(&h->ev[0]) != cudaSuccess || cudaEventCreate(&h->ev[1]) != cudaSuccess))
         rc = fail(TRAJOPT_E_CUDA, "cudaEventCreate failed");
@@ -224,6 +225,24 @@ int trajopt_set_reference(trajopt_handle* h, const double* h_q_ref, const double
         }
     }
     CUDA_OK(cudaMemcpy(h->d_ref, rows.data(), rows.size() * sizeof(double), cudaMemcpyHostToDevice));
+    h->w.ref_batch = nullptr;      // back to the shared reference
+    h->have_ref = true;
+    h->begun = false;
+    return 0;
+}
+
+int trajopt_set_reference_batch(trajopt_handle* h, const double* d_q_ref, const double* d_xi_ref, void* stream) {
+    if (!h || !d_q_ref || !d_xi_ref) return fail(TRAJOPT_E_INVALID, "trajopt_set_reference_batch: NULL argument");
+    DeviceGuard guard(h->device);
+    if (!h->d_ref_batch) {
+        void* q = nullptr;
+        CUDA_OK(cudaMalloc(&q, ((size_t)h->N + 1) * h->REFROW * (size_t)h->Bp * sizeof(double)));
+        h->allocs.push_back(q);
+        h->d_ref_batch = (double*)q;
+    }
+    int rc = DISPATCH_KIND(h, set_reference_batch_impl, h, d_q_ref, d_xi_ref, (cudaStream_t)stream);
+    if (rc) return rc;
+    h->w.ref_batch = h->d_ref_batch;
     h->have_ref = true;
     h->begun = false;
     return 0;

@@ -47,6 +47,7 @@ struct trajopt_handle {
     std::vector<void*> allocs;
     void* hist_allocs[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     double* d_ref = nullptr;
+    double* d_ref_batch = nullptr;   // per-problem references, allocated on first use
     double* d_dweight = nullptr;
     int* h_counters = nullptr;   // pinned
     // host staging for trajopt_solve_host
@@ -135,7 +136,8 @@ template <int KIND, bool MS>
 int run_linearize(trajopt_handle* h, cudaStream_t s) {
     PhaseTimer t(h, s, PH_LIN);
     dim3 grid(blocks_for(h->Bp, 128), h->N + 1);
-    LAUNCH((k_linearize<KIND, MS>), grid, 128, 0, s, h->prm, h->w);
+    if (h->w.ref_batch) LAUNCH((k_linearize<KIND, MS, true>), grid, 128, 0, s, h->prm, h->w);
+    else LAUNCH((k_linearize<KIND, MS, false>), grid, 128, 0, s, h->prm, h->w);
     return 0;
 }
 
@@ -299,6 +301,7 @@ inline int maybe_compact(trajopt_handle* h, cudaStream_t s, int act) {
     P_(w.iters, 1); P_(w.status, 1); P_(w.ls_state, 1);
     P_(w.Jhist, mi); P_(w.gradhist, mi + 1); P_(w.defhist, mi + 1); P_(w.alphahist, mi);
     P_(h->d_dweight, 1);
+    if (h->w.ref_batch) P_(h->d_ref_batch, Np1 * h->REFROW);
     if (h->method == TRAJOPT_AL_MS) {
         P_(w.lam, Np1 * 2 * h->NU); P_(w.imu, Np1 * 2 * h->NU);
         P_(w.al_mu, 1); P_(w.al_outer, 1); P_(w.al_viol, 1); P_(w.al_done, 1);
@@ -422,6 +425,13 @@ int debug_linearize_impl(trajopt_handle* h, double* Fx, double* Fu, double* dd, 
 }
 
 template <int KIND>
+int set_reference_batch_impl(trajopt_handle* h, const double* d_q, const double* d_xi, cudaStream_t s) {
+    dim3 grid(blocks_for(h->Bp, 128), h->N + 1);
+    LAUNCH((k_pack_ref_batch<KIND>), grid, 128, 0, s, h->B, h->Bp, h->N + 1, d_q, d_xi, h->d_ref_batch);
+    return 0;
+}
+
+template <int KIND>
 int debug_stage_impl(trajopt_handle* h, int i, int terminal, int n, const double* x, const double* u, double* f,
                      double* Fx, double* Fu, double* l, double* lx, double* lxx, double* lu, double* err, cudaStream_t s) {
     LAUNCH((k_debug_stage<KIND>), blocks_for(n, 64), 64, 0, s, h->prm, h->d_ref, i, terminal, n, x, u, f, Fx, Fu, l, lx,
@@ -460,6 +470,7 @@ inline int ensure_hist(trajopt_handle* h) {
 
 // the four entry points api.cu dispatches on the family
 #define TRAJOPT_KIND_INSTANTIATE(K)                                                                                             \
+    template int trajopt_host::set_reference_batch_impl<K>(trajopt_handle*, const double*, const double*, cudaStream_t);        \
     template int trajopt_host::begin_impl<K>(trajopt_handle*, const double*, const double*, int, cudaStream_t);                  \
     template int trajopt_host::iterate_impl<K>(trajopt_handle*, int, int*, cudaStream_t);                                        \
     template int trajopt_host::debug_linearize_impl<K>(trajopt_handle*, double*, double*, double*, double*, double*, double*,   \
@@ -467,6 +478,7 @@ inline int ensure_hist(trajopt_handle* h) {
     template int trajopt_host::debug_stage_impl<K>(trajopt_handle*, int, int, int, const double*, const double*, double*,       \
                                                    double*, double*, double*, double*, double*, double*, double*, cudaStream_t);
 #define TRAJOPT_KIND_EXTERN(K)                                                                                                  \
+    extern template int trajopt_host::set_reference_batch_impl<K>(trajopt_handle*, const double*, const double*, cudaStream_t); \
     extern template int trajopt_host::begin_impl<K>(trajopt_handle*, const double*, const double*, int, cudaStream_t);           \
     extern template int trajopt_host::iterate_impl<K>(trajopt_handle*, int, int*, cudaStream_t);                                 \
     extern template int trajopt_host::debug_linearize_impl<K>(trajopt_handle*, double*, double*, double*, double*, double*,     \

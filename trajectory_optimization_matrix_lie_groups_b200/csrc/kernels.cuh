@@ -18,7 +18,8 @@ struct Work {
     double* X[2];        // [N+1][NS][Bp] x 2 (current / candidate, selected per problem by sel)
     double* U[2];        // [N][NU][Bp]  x 2
     int* sel;            // [Bp] which buffer holds the current trajectory
-    const double* ref;   // [N+1][RefRow]
+    const double* ref;   // [N+1][RefRow]  reference shared by the batch
+    const double* ref_batch;   // [N+1][RefRow][Bp] per-problem references (NULL: shared), see trajopt_set_reference_batch
     double* lin;         // [Bp/32][N+1][LinRec::LEN][32] (group-major, see LinRec)
     double* Lc;          // [N+1][Bp] stage costs of the current trajectory
     double* Dsq;         // [N][Bp]   squared defect norm per stage
@@ -174,6 +175,81 @@ __host__ __device__ constexpr int tri_idx(int n, int r, int c) {   // packed upp
 __host__ __device__ constexpr int sym_idx(int n, int r, int c) { return r <= c ? tri_idx(n, r, c) : tri_idx(n, c, r); }
 
 // ------------------------------------------------------------------------------------------
+// Reference row of (stage, problem): the batch-shared row (uniform loads) or the problem's own (coalesced SoA)
+// ------------------------------------------------------------------------------------------
+template <int KIND>
+TO_DEV void fetch_ref_row(const Work& w, int Bp, int stage, int b, double (&rr)[RefRow<KIND>::N]) {
+    constexpr int RR = RefRow<KIND>::N;
+    if (w.ref_batch) {
+        const double* p = w.ref_batch + (size_t)stage * RR * Bp + b;
+#pragma unroll
+        for (int j = 0; j < RR; ++j) rr[j] = p[(size_t)j * Bp];
+    } else {
+        const double* p = w.ref + (size_t)stage * RR;
+#pragma unroll
+        for (int j = 0; j < RR; ++j) rr[j] = p[j];
+    }
+}
+
+// Per-problem references arrive problem-major ([B][N+1][7|4] poses as quaternion (+ position), [B][N+1][6|3] twists);
+// this packs them into the rows the cost reads (same arithmetic, operation by operation, as the host packing of the
+// shared reference in trajopt_set_reference: no FMA contraction, IEEE sqrt and division).
+template <int KIND>
+__global__ void k_pack_ref_batch(int B, int Bp, int Np1, const double* __restrict__ q_in, const double* __restrict__ xi_in,
+                                 double* __restrict__ out) {
+    constexpr int RR = RefRow<KIND>::N, NPOSE = on_so3(KIND) ? 4 : 7, NV = Dims<KIND>::NX - Dims<KIND>::NP;
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const int stage = blockIdx.y;
+    if (b >= Bp) return;
+    double r[RR];
+#pragma unroll
+    for (int j = 0; j < RR; ++j) r[j] = 0.0;
+    r[3] = 1.0;
+    if (b < B) {
+        const double* q = q_in + ((size_t)b * Np1 + stage) * NPOSE;
+        const double* xi = xi_in + ((size_t)b * Np1 + stage) * NV;
+        const double n2 = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(q[0], q[0]), __dmul_rn(q[1], q[1])), __dmul_rn(q[2], q[2])),
+                                    __dmul_rn(q[3], q[3]));
+        const double nq = __dsqrt_rn(n2);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) r[j] = __ddiv_rn(q[j], nq);
+        double* R;
+        if constexpr (on_so3(KIND)) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) r[4 + j] = xi[j];
+            R = r + 7;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) r[4 + j] = q[4 + j];
+#pragma unroll
+            for (int j = 0; j < 6; ++j) r[7 + j] = xi[j];
+            R = r + 13;
+        }
+        {   // Eigen::Quaternion::toRotationMatrix, operation by operation
+            const double x = r[0], y = r[1], z = r[2], w_ = r[3];
+            const double tx = __dmul_rn(2.0, x), ty = __dmul_rn(2.0, y), tz = __dmul_rn(2.0, z);
+            const double twx = __dmul_rn(tx, w_), twy = __dmul_rn(ty, w_), twz = __dmul_rn(tz, w_);
+            const double txx = __dmul_rn(tx, x), txy = __dmul_rn(ty, x), txz = __dmul_rn(tz, x);
+            const double tyy = __dmul_rn(ty, y), tyz = __dmul_rn(tz, y), tzz = __dmul_rn(tz, z);
+            R[0] = __dsub_rn(1.0, __dadd_rn(tyy, tzz)); R[1] = __dsub_rn(txy, twz); R[2] = __dadd_rn(txz, twy);
+            R[3] = __dadd_rn(txy, twz); R[4] = __dsub_rn(1.0, __dadd_rn(txx, tzz)); R[5] = __dsub_rn(tyz, twx);
+            R[6] = __dsub_rn(txz, twy); R[7] = __dadd_rn(tyz, twx); R[8] = __dsub_rn(1.0, __dadd_rn(txx, tyy));
+        }
+        if constexpr (!on_so3(KIND)) {
+            const double* pp = r + 4;   // [p]x R
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                r[22 + j] = __dsub_rn(__dmul_rn(pp[1], R[6 + j]), __dmul_rn(pp[2], R[3 + j]));
+                r[25 + j] = __dsub_rn(__dmul_rn(pp[2], R[j]), __dmul_rn(pp[0], R[6 + j]));
+                r[28 + j] = __dsub_rn(__dmul_rn(pp[0], R[3 + j]), __dmul_rn(pp[1], R[j]));
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < RR; ++j) out[((size_t)stage * RR + j) * Bp + b] = r[j];
+}
+
+// ------------------------------------------------------------------------------------------
 // Initialisation
 // ------------------------------------------------------------------------------------------
 template <int KIND>
@@ -258,7 +334,9 @@ __global__ void k_init_ms(const Params prm, Work w, bool only_running) {
             for (int j = 0; j < 3; ++j) s.xi[j] = w.x0[(size_t)(4 + j) * prm.Bp + b];
         }
     } else {
-        load_ref_state<KIND>(w.ref, stage, s);
+        double rr[RefRow<KIND>::N];
+        fetch_ref_row<KIND>(w, prm.Bp, stage, b, rr);
+        load_ref_state<KIND>(rr, 0, s);
     }
     store_state<KIND>(w.X[0], stage, prm.Bp, b, s);
     if (stage < prm.N) {
@@ -303,7 +381,8 @@ __global__ void __launch_bounds__(kBlock) k_init_ss(const Params prm, Work w) {
 // ------------------------------------------------------------------------------------------
 // Stage-parallel linearisation.  grid = (ceil(Bp/128), N+1), thread = (problem, stage)
 // ------------------------------------------------------------------------------------------
-template <int KIND, bool MS>
+// REFB: per-problem references (a separate instantiation keeps the shared-reference kernel's register budget intact)
+template <int KIND, bool MS, bool REFB>
 __global__ void __launch_bounds__(128) k_linearize(const Params prm, Work w) {
     using D = Dims<KIND>;
     using LR = LinRec<KIND>;
@@ -314,7 +393,18 @@ __global__ void __launch_bounds__(128) k_linearize(const Params prm, Work w) {
     const int Bp = prm.Bp;
     const double* X = w.X[w.sel[b]];
     const double* U = w.U[w.sel[b]];
-    const double* refrow = w.ref + (size_t)stage * RefRow<KIND>::N;
+    double rr[REFB ? RefRow<KIND>::N : 1];
+    const double* refrow;
+    if constexpr (REFB) {
+        constexpr int RR = RefRow<KIND>::N;
+        const double* p = w.ref_batch + (size_t)stage * RR * Bp + b;
+#pragma unroll
+        for (int j = 0; j < RR; ++j) rr[j] = p[(size_t)j * Bp];
+        refrow = rr;
+    } else {
+        (void)rr;
+        refrow = w.ref + (size_t)stage * RefRow<KIND>::N;
+    }
     double* out = w.lin;
 
     State<KIND> x;

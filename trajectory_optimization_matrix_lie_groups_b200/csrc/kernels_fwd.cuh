@@ -53,7 +53,8 @@ __global__ void __launch_bounds__(kBlock) k_forward(const Params prm, Work w, in
     double J = 0.0, dsq = 0.0;
 
     for (int i = 0; i < N; ++i) {
-        const double* refrow = w.ref + (size_t)i * RefRow<KIND>::N;
+        double refrow[RefRow<KIND>::N];
+        if (COST) fetch_ref_row<KIND>(w, Bp, i, b, refrow);
         double dx[NX];
         state_minus<KIND>(xnew, x, dx);
         double u[NU], unew[NU], du[NU];
@@ -159,7 +160,8 @@ __global__ void __launch_bounds__(kBlock) k_forward(const Params prm, Work w, in
         x = xnext;
     }
     if (COST) {
-        const double* refrow = w.ref + (size_t)N * RefRow<KIND>::N;
+        double refrow[RefRow<KIND>::N];
+        fetch_ref_row<KIND>(w, Bp, N, b, refrow);
         J = J + stage_cost<KIND>(prm, xnew, nullptr, refrow, true);
         w.Jcand[(size_t)ai * Bp + b] = J;
         if (MS) w.Jcand[(size_t)(prm.n_alphas + ai) * Bp + b] = sqrt(dsq);

@@ -110,6 +110,14 @@ class BatchSolver:
             raise ValueError(f"reference shapes {q.shape}, {xi.shape} do not match N={self.N}, kind={self.kind}")
         check(lib.trajopt_set_reference(self._h, q.ctypes.data_as(C.c_void_p), xi.ctypes.data_as(C.c_void_p)))
 
+    def set_reference_batch(self, q_ref_rows, xi_ref):
+        """One reference per problem: q_ref_rows (B, N+1, 7|4) quat[+pos] rows, xi_ref (B, N+1, 6|3)."""
+        npose, nv = self.NS - (self.NX - self.NP), self.NX - self.NP
+        q = self._dev(q_ref_rows, (self.B, self.N + 1, npose))
+        xi = self._dev(xi_ref, (self.B, self.N + 1, nv))
+        check(lib.trajopt_set_reference_batch(self._h, _ptr(q), _ptr(xi), _stream(self.device)))
+        torch.cuda.current_stream(self.device).synchronize()      # q, xi may be temporaries
+
     # ------------------------------------------------------------------------------------ solving
     def _dev(self, a, shape=None, dtype=torch.float64):
         t = torch.as_tensor(a, dtype=dtype)

@@ -124,6 +124,12 @@ class _NativeController(BaseController):
             s.set_params(Q=cost.Q, R=cost.R, P=cost.P, **_native.dynamics_params(self._kind, self.dynamics), **params)
         return s
 
+    def _xi_ref_array(self):
+        from . import manif_compat
+        if self._kind in ("so3", "pendulum"):
+            return np.asarray([manif_compat.so3_vel(w) for w in self._xi_ref])
+        return np.asarray(self._xi_ref, dtype=float)
+
     def _params(self, n_iterations, tol_grad_norm, tol_d_norm=1e-6):
         return dict(max_iters=n_iterations, tol_grad_norm=tol_grad_norm, tol_d_norm=tol_d_norm,
                     max_reg=self._mu_max if self._mu_max else 0.0, rollout=self._rollout_mode,
@@ -144,11 +150,14 @@ class _NativeController(BaseController):
 
     # -------------------------------------------------------------------------------- fit_batch
     def fit_batch(self, x0_batch, us_init=None, n_iterations=100, tol_grad_norm=None, tol_d_norm=1e-6,
-                  return_trajectories=True, return_hist=False, device=None, shard=None, **extra):
+                  return_trajectories=True, return_hist=False, device=None, shard=None, q_ref_batch=None,
+                  xi_ref_batch=None, **extra):
         """Solve B problems that differ in their initial state (and optionally initial controls).
 
         x0_batch: list of reference-style states [q, xi], or an array of device rows (B, NS).
         us_init:  None (zeros), (N, m) shared, or (B, N, m).
+        q_ref_batch, xi_ref_batch: one reference per problem — (B, N+1, 4, 4) poses (or (B, N+1, 3, 3) / device rows)
+                  and (B, N+1, 6|3) twists; default: the controller's own reference for every problem.
         shard:    split the batch over the ranks of the initialised torch.distributed job
                   (default: yes when a job is initialised); summaries are all-gathered, trajectories
                   stay on the rank that solved them.
@@ -163,13 +172,28 @@ class _NativeController(BaseController):
             shard = ws > 1
         params = self._params(n_iterations, tol_grad_norm, tol_d_norm)
         params.update(extra)
+        if (q_ref_batch is None) != (xi_ref_batch is None):
+            raise ValueError("q_ref_batch and xi_ref_batch go together")
+
+        def ready(b, lo_):
+            """solver for b problems starting at global index lo_, with the per-problem references of that range"""
+            sv = self._solver(b, device, **params)
+            if q_ref_batch is not None:
+                q = np.asarray(q_ref_batch)[lo_:lo_ + b, :self.N + 1]
+                so3 = self._kind in ("so3", "pendulum")
+                q_rows = q if q.shape[-1] in (4, 7) and q.ndim == 3 else _native.layout.pose_rows(so3, q)
+                sv.set_reference_batch(q_rows, np.asarray(xi_ref_batch, dtype=float)[lo_:lo_ + b, :self.N + 1])
+            else:
+                sv.set_reference(_native.ref_rows(self._kind, self._q_ref)[:self.N + 1], self._xi_ref_array()[:self.N + 1])
+            return sv
         if shard and ws > 1:
-            out, summ, (lo, hi) = _dist.solve_sharded(lambda b: self._solver(b, device, **params), rows, us_init,
+            lo, hi = _dist.shard_bounds(B, rank, ws)
+            out, summ, (lo, hi) = _dist.solve_sharded(lambda b: ready(b, lo), rows, us_init,
                                                       trajectories=return_trajectories)
             s = self._solver(hi - lo, device, **params)
         else:
             lo, hi = 0, B
-            s = self._solver(B, device, **params)
+            s = ready(B, 0)
             out = s.solve(rows, us_init, trajectories=return_trajectories)
             summ = out
         res = BatchResult(self._kind, *(summ[k].cpu().numpy() for k in ("J", "iters", "status", "grad", "defect")),
