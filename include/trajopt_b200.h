@@ -90,6 +90,11 @@ typedef struct trajopt_params {
     int32_t n_al_iters;
     double al_mu0, al_mu_scale, al_mu_max, tol_constr;
     double length;           /* Pendulum3dDyanmics length of the stick (traopt_dynamics.py:459); ignored otherwise */
+    /* AL only, beyond the reference (which has InputConstraint only, traopt_constraints.py:66-169): box bounds on the
+     * body velocity xi = [omega, v], handled by the same BaseConstraint / ALConstrainedCost algebra
+     * (g = [lb - xi; xi - ub], g_x = [0 -I; 0 I], traopt_cost.py:1236-1320); active at the terminal stage too */
+    double xi_lb[6], xi_ub[6];
+    int32_t has_state_bounds;
 } trajopt_params;
 
 const char* trajopt_last_error(void);
@@ -118,6 +123,8 @@ int trajopt_export(trajopt_handle* h, double* d_xs, double* d_us, double* d_J, i
  * d_defect_hist [B][max_iters+1], d_alpha_hist [B][max_iters] (accepted step index, -1 none) */
 int trajopt_export_hist(trajopt_handle* h, double* d_J_hist, double* d_grad_hist, double* d_defect_hist,
                         int32_t* d_alpha_hist, void* stream);
+/* AL with velocity bounds: d_lmbd_state [B][N+1][2NV], d_imu_state [B][N+1][2NV] */
+int trajopt_export_al_state(trajopt_handle* h, double* d_lmbd_state, double* d_imu_state, void* stream);
 /* regulariser state after the last backward pass: d_mu [B], d_delta [B] (traopt_controller.py:1899-1900,
  * 2233-2246; `mu` is what the on_iteration callbacks receive) */
 int trajopt_export_reg(trajopt_handle* h, double* d_mu, double* d_delta, void* stream);

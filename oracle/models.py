@@ -370,6 +370,38 @@ class InputConstraint:
         return np.vstack([-np.identity(self.action_size), np.identity(self.action_size)])  # :167-169
 
 
+class InputVelocityConstraint(InputConstraint):
+    """Box bounds on u AND on the body velocity xi (NOT in the reference, which has InputConstraint only): the same
+    BaseConstraint interface (traopt_constraints.py:5-63), g = [lb_u - u; u - ub_u; lb_xi - xi; xi - ub_xi],
+    g_x = [0 0; 0 0; 0 -I; 0 I], g_u = [-I; I; 0; 0].  The velocity rows stay active at the terminal stage."""
+
+    def __init__(self, input_lb, input_ub, xi_lb, xi_ub, state_size=12, action_size=6):
+        super().__init__(input_lb, input_ub, state_size, action_size)
+        self.nv = state_size // 2
+        self.xlb = np.broadcast_to(np.asarray(xi_lb, dtype=float), (self.nv,)).copy()
+        self.xub = np.broadcast_to(np.asarray(xi_ub, dtype=float), (self.nv,)).copy()
+        self.constr_size = 2 * action_size + 2 * self.nv
+
+    def g(self, x, u, i, terminal=False):
+        xi = np.asarray(x[1], dtype=float)
+        gu = np.zeros(2 * self.action_size) if terminal else np.concatenate([self.lb - u, u - self.ub])
+        return np.concatenate([gu, self.xlb - xi, xi - self.xub])
+
+    def g_x(self, x, u, i, terminal=False):
+        G = np.zeros((self.constr_size, self.state_size))
+        m2, nv, npose = 2 * self.action_size, self.nv, self.state_size - self.nv
+        G[m2:m2 + nv, npose:] = -np.identity(nv)
+        G[m2 + nv:, npose:] = np.identity(nv)
+        return G
+
+    def g_u(self, x, u, i, terminal=False):
+        G = np.zeros((self.constr_size, self.action_size))
+        if not terminal:
+            G[:self.action_size] = -np.identity(self.action_size)
+            G[self.action_size:2 * self.action_size] = np.identity(self.action_size)
+        return G
+
+
 class ALConstrainedCost:
     """traopt_cost.py:1173-1320: l + lambda^T g + 1/2 g^T Imu g and its derivatives."""
 

@@ -170,3 +170,25 @@ def test_fit_batch_with_per_problem_references():
         ctrl_b = tc.iLQR_Tracking_SE3_MS(dyn, cost_b, Nh, qb[b], xb[b], rollout="nonlinear")
         xs, us, *_ = ctrl_b.fit(x0, np.zeros((Nh, 6)), n_iterations=60, tol_grad_norm=1e-10)
         assert np.max(np.abs(us - res.us[b])) < 1e-9
+
+
+def test_al_controller_with_velocity_bounds():
+    from trajectory_optimization_matrix_lie_groups_b200 import workloads
+    from trajectory_optimization_matrix_lie_groups_b200.traoptlibrary import (traopt_constraints, traopt_controller as tc,
+                                                                              traopt_cost, traopt_dynamics)
+    N, dt = 40, 0.01
+    q_ref, xi_ref = workloads.helix_reference(N, dt)
+    Q = np.diag([10.0, 10, 10, 1, 1, 1, 1, 1, 1, 1, 1, 1])
+    dyn = traopt_dynamics.SE3Dynamics(np.diag([0.5, 0.7, 0.9, 1.0, 1.0, 1.0]), dt)
+    cost = traopt_cost.SE3TrackingQuadraticGaussNewtonCost(Q, 1e-3 * np.eye(6), 10 * Q, q_ref, xi_ref)
+    con = traopt_constraints.InputVelocityConstraint(-30.0, 30.0, [-5, -5, -0.5, -5, -5, -5], [5, 5, 0.5, 5, 5, 5])
+    ctrl = tc.AL_iLQR_Tracking_SE3_MS(dyn, cost, con, N, q_ref, xi_ref)
+    T0 = np.eye(4)
+    T0[:3, 3] = [-0.3, -0.3, -0.1]
+    seen = []
+    out = ctrl.fit([T0, np.array([0, 0, 0.1, 2.0, 0, 0.2])], np.zeros((N, 6)), n_al_iters=12, n_ilqr_iters=60,
+                   on_iteration_al=lambda it, conv, lmbd, Imu, mu, ce, *h: seen.append((conv, lmbd.shape, Imu.shape, ce.shape, float(ce.max()))))
+    xs = out[0]
+    assert seen[-1][0] and len(seen) == 6                       # oracle: 6 outer iterations
+    assert seen[0][1:4] == ((N + 1, 24), (N + 1, 24, 24), (N + 1, 24))
+    assert max(abs(x[1][2]) for x in xs) < 0.5 + 1e-2          # omega_z respects its bound

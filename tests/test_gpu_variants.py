@@ -231,3 +231,48 @@ def test_max_iters_zero_and_shared_us_init():
     for i in range(N):
         xs.append(dyn.f(xs[i], us0[i], i))
     assert gc.quat_rows_close(out["xs"][1].cpu().numpy(), gc.oracle_rows("se3", xs), 0) < 1e-12
+
+
+def test_augmented_lagrangian_with_velocity_bounds():
+    """Velocity box bounds next to the input bounds (an addition to the reference, same AL algebra): device vs oracle."""
+    from trajectory_optimization_matrix_lie_groups_b200 import BatchSolver, layout, workloads
+    N, dt, B = 40, 0.01, 3
+    q_ref, xi_ref = workloads.helix_reference(N, dt)
+    J = np.diag([0.5, 0.7, 0.9, 1.0, 1.0, 1.0])
+    Q = np.diag([10.0, 10, 10, 1, 1, 1, 1, 1, 1, 1, 1, 1])
+    R = 1e-3 * np.eye(6)
+    P = 10 * Q
+    lb, ub = -30.0, 30.0
+    xlb = np.array([-5.0, -5, -0.5, -5, -5, -5])     # the reference spins at omega_z = 1: this bound becomes active
+    xub = -xlb
+    rng = np.random.default_rng(24234156)
+    X0 = workloads.perturb_se3(np.eye(3), np.array([-0.3, -0.3, -0.1]), np.array([0, 0, 0.1, 2.0, 0, 0.2]), B, 0.02, rng)
+    n_al, n_ilqr = 12, 60
+    s = BatchSolver("se3", "al_ms", N, B)
+    s.set_params(dt=dt, Ib=J[:3, :3], mass=1.0, Q=Q, R=R, P=P, max_iters=n_ilqr, tol_grad_norm=1e-6, tol_d_norm=1e-6,
+                 lb=lb, ub=ub, xi_lb=xlb, xi_ub=xub, n_al_iters=n_al, tol_constr=1e-2)
+    s.set_reference(layout.pose_rows(False, q_ref), xi_ref)
+    out = s.solve(X0)
+    al = {k: v.cpu().numpy() for k, v in s.export_al().items()}
+    us = out["us"].cpu().numpy()
+    xs = out["xs"].cpu().numpy()
+    dyn = models.SE3Dynamics(J, dt)
+    cost = models.SE3TrackingQuadraticGaussNewtonCost(Q, R, P, q_ref, xi_ref)
+    con = models.InputVelocityConstraint(np.full(6, lb), np.full(6, ub), xlb, xub)
+    active = False
+    for b in range(B):
+        alc = models.ALConstrainedCost(cost, con, N)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            r = solvers.al_ilqr_ms(dyn, alc, con, solvers.SE3Group, N, [T for T in q_ref], xi_ref,
+                                   gc.oracle_state("se3", X0[b]), np.zeros((N, 6)), n_al_iters=n_al, n_ilqr_iters=n_ilqr,
+                                   tol_constr=1e-2)
+        assert int(al["outer_iters"][b]) == r.outer_iterations, (b, al["outer_iters"][b], r.outer_iterations)
+        assert int(out["iters"][b]) == r.inner.iterations
+        assert abs(al["violation"][b] - r.violation_hist[-1]) < 1e-6 * max(1.0, abs(r.violation_hist[-1]))
+        assert np.max(np.abs(us[b] - r.inner.us)) < 1e-6
+        assert gc.quat_rows_close(xs[b], gc.oracle_rows("se3", r.inner.xs), 0) < 1e-6
+        lm = np.concatenate((al["lmbd"][b], al["lmbd_state"][b]), axis=1)
+        assert np.max(np.abs(lm - r.lmbd)) < 1e-5 * max(1.0, np.max(np.abs(r.lmbd)))
+        active |= r.outer_iterations > 1 and np.max(r.lmbd[:, 12:]) > 0
+    assert active, "the velocity bounds never became active"

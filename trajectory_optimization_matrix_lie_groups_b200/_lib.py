@@ -54,6 +54,9 @@ class Params(C.Structure):
         ("al_mu_max", C.c_double),
         ("tol_constr", C.c_double),
         ("length", C.c_double),
+        ("xi_lb", C.c_double * 6),
+        ("xi_ub", C.c_double * 6),
+        ("has_state_bounds", C.c_int32),
     ]
 
 
@@ -74,6 +77,7 @@ SYMBOLS = {
     "trajopt_export_hist": (_I, [_P, _P, _P, _P, _P, _P]),
     "trajopt_export_al": (_I, [_P, _P, _P, _P, _P, _P, _P]),
     "trajopt_export_reg": (_I, [_P, _P, _P, _P]),
+    "trajopt_export_al_state": (_I, [_P, _P, _P, _P]),
     "trajopt_solve": (_I, [_P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
     "trajopt_solve_host": (_I, [_P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
     "trajopt_debug_linearize": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P]),

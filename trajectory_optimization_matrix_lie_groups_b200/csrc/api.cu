@@ -177,7 +177,15 @@ int trajopt_set_params(trajopt_handle* h, const trajopt_params* p) {
             for (int r = 0; r < NV; ++r) sacc = std::fma(q.Bv[r * NU + a], q.Bv[r * NU + c], sacc);
             q.BtB[a * NU + c] = sacc;
         }
-    for (int j = 0; j < 6; ++j) { q.lb[j] = p->lb[j]; q.ub[j] = p->ub[j]; }
+    for (int j = 0; j < 6; ++j) { q.lb[j] = p->lb[j]; q.ub[j] = p->ub[j]; q.xlb[j] = p->xi_lb[j]; q.xub[j] = p->xi_ub[j]; }
+    q.has_state_bounds = (h->method == TRAJOPT_AL_MS && p->has_state_bounds) ? 1 : 0;
+    if (q.has_state_bounds && !h->w.lam_s) {
+        const size_t Np1 = (size_t)h->N + 1, nv = (size_t)(h->NX - h->NP), Bp = (size_t)h->Bp;
+        int rc2 = dalloc(h, &h->w.lam_s, Np1 * 2 * nv * Bp);
+        if (!rc2) rc2 = dalloc(h, &h->w.imu_s, Np1 * 2 * nv * Bp);
+        if (!rc2) rc2 = dalloc(h, &h->w.lxxv, Np1 * nv * Bp);
+        if (rc2) return rc2;
+    }
     q.tol_grad = p->tol_grad_norm;
     q.tol_defect = p->tol_d_norm;
     q.mu_min = 1e-6;          // traopt_controller.py:1863-1866
@@ -324,6 +332,19 @@ int trajopt_export_al(trajopt_handle* h, double* d_lmbd, double* d_imu, double* 
     if (d_mu) LAUNCH(k_export_rows<double>, dim3(bg, 1), 128, 0, s, h->B, h->Bp, 1, w.al_mu, (const int*)h->w.orig, d_mu);
     if (d_violation) LAUNCH(k_export_rows<double>, dim3(bg, 1), 128, 0, s, h->B, h->Bp, 1, w.al_viol, (const int*)h->w.orig, d_violation);
     if (d_outer_iters) LAUNCH(k_export_rows<int>, dim3(bg, 1), 128, 0, s, h->B, h->Bp, 1, w.al_outer, (const int*)h->w.orig, (int*)d_outer_iters);
+    return 0;
+}
+
+int trajopt_export_al_state(trajopt_handle* h, double* d_lmbd_state, double* d_imu_state, void* stream) {
+    if (!h) return fail(TRAJOPT_E_INVALID, "trajopt_export_al_state: NULL handle");
+    if (h->method != TRAJOPT_AL_MS || !h->prm.has_state_bounds) return fail(TRAJOPT_E_STATE, "trajopt_export_al_state: no velocity bounds on this handle");
+    if (!h->begun) return fail(TRAJOPT_E_STATE, "trajopt_export_al_state: nothing solved yet");
+    DeviceGuard guard(h->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    const Work& w = h->w;
+    const int bg = blocks_for(h->Bp, 128), cw = 2 * (h->NX - h->NP);
+    if (d_lmbd_state) LAUNCH(k_export_traj, dim3(bg, h->N + 1), 128, 0, s, h->B, h->Bp, cw, w.lam_s, w.lam_s, (const int*)nullptr, (const int*)h->w.orig, d_lmbd_state, h->N + 1);
+    if (d_imu_state) LAUNCH(k_export_traj, dim3(bg, h->N + 1), 128, 0, s, h->B, h->Bp, cw, w.imu_s, w.imu_s, (const int*)nullptr, (const int*)h->w.orig, d_imu_state, h->N + 1);
     return 0;
 }
 

@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(LPW) k_backward(const Params prm, Work w, int 
             for (int c = r; c < NX; ++c) {
                 double v;
                 if (c < NP) v = rec[(size_t)(LR::LXX_OFF + tri_idx(NP, r, c)) * kRecStride];
-                else if (r >= NP) v = 2.0 * prm.P2[(r - NP) * NV + (c - NP)];
+                else if (r >= NP) v = 2.0 * prm.P2[(r - NP) * NV + (c - NP)] + ((r == c && prm.has_state_bounds) ? w.lxxv[soa(N, r - NP, NV, (int)Bp, b)] : 0.0);
                 else v = 0.0;
                 Vs[tri_idx(NX, r, c) * LPW] = v;
             }
@@ -455,7 +455,7 @@ __global__ void __launch_bounds__(LPW) k_backward(const Params prm, Work w, int 
                         double s = 0.0;
                         if (r <= c) {
                             if (c < NP) s = rec[(size_t)(LR::LXX_OFF + tri_idx(NP, r, c)) * kRecStride];
-                            else if (r >= NP) s = 2.0 * prm.W2[(r - NP) * NV + (c - NP)];
+                            else if (r >= NP) s = 2.0 * prm.W2[(r - NP) * NV + (c - NP)] + ((r == c && prm.has_state_bounds) ? w.lxxv[soa(i, r - NP, NV, (int)Bp, b)] : 0.0);
                         }
                         acc[ii][j] = s;
                     }

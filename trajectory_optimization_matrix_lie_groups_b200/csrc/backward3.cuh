@@ -428,7 +428,7 @@ __global__ void __launch_bounds__(kB3Threads, 4) k_backward3(const Params prm, W
             for (int c = r; c < NX; ++c) {
                 double v;
                 if (c < NP) v = g[(size_t)(LR::LXX_OFF + tri_idx(NP, r, c)) * kRecStride];
-                else if (r >= NP) v = 2.0 * prm.P2[(r - NP) * NV + (c - NP)];
+                else if (r >= NP) v = 2.0 * prm.P2[(r - NP) * NV + (c - NP)] + ((r == c && prm.has_state_bounds) ? w.lxxv[soa(N, r - NP, NV, (int)Bp, b)] : 0.0);
                 else v = 0.0;
                 Vs[tri_idx(NX, r, c) * 32] = v;
             }
@@ -631,6 +631,10 @@ __global__ void __launch_bounds__(kB3Threads, 4) k_backward3(const Params prm, W
 #pragma unroll
             for (int j = 0; j < 3; ++j) vx2[j] -= yq[j];
             b3_block_cb<KIND, 2, 2, true, true>(prm, rec, grec, X, Ys, Yk, h22);
+            if (prm.has_state_bounds) {
+#pragma unroll
+                for (int j = 0; j < 3; ++j) h22[j][j] += w.lxxv[soa(i, j, NV, (int)Bp, b)];
+            }
             __syncthreads();   // (2) every X is formed: V and V_x may be overwritten; Y_3 visible
             b3_store_block<KIND, 0, 0>(Vs, h00);
             b3_store_block<KIND, 2, 2>(Vs, h22);
@@ -678,6 +682,10 @@ __global__ void __launch_bounds__(kB3Threads, 4) k_backward3(const Params prm, W
 #pragma unroll
             for (int j = 0; j < 3; ++j) vx3[j] -= yq[j];
             b3_block_cb<KIND, 3, 3, false, false>(prm, rec, grec, X, Ys, Yk, h33);
+            if (prm.has_state_bounds) {
+#pragma unroll
+                for (int j = 0; j < 3; ++j) h33[j][j] += w.lxxv[soa(i, 3 + j, NV, (int)Bp, b)];
+            }
             __syncthreads();   // (2)
             b3_store_block<KIND, 1, 1>(Vs, h11);
             b3_store_block<KIND, 0, 1>(Vs, h01);

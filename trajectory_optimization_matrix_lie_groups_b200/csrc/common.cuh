@@ -73,6 +73,8 @@ struct Params {
     double Bv[36];               // (NP x NU) velocity rows of f_u = Jinv * Pu * dt  (row-major, leading dim NU)
     double BtB[36];              // Bv^T Bv (NU x NU): what mu * I adds to Q_uu (traopt_controller.py:2311-2313)
     double lb[6], ub[6];
+    double xlb[6], xub[6];       // AL: box bounds on the velocity part of the state
+    int has_state_bounds;
     double tol_grad, tol_defect;
     double mu_min, mu_max, delta0;           // Levenberg-Marquardt schedule
     double defect_mu0, defect_rho, defect_gamma, defect_kappa;   // MS merit line search constants

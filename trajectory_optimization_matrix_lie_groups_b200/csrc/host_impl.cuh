@@ -304,6 +304,7 @@ inline int maybe_compact(trajopt_handle* h, cudaStream_t s, int act) {
     if (h->w.ref_batch) P_(h->d_ref_batch, Np1 * h->REFROW);
     if (h->method == TRAJOPT_AL_MS) {
         P_(w.lam, Np1 * 2 * h->NU); P_(w.imu, Np1 * 2 * h->NU);
+        if (h->prm.has_state_bounds) { P_(w.lam_s, Np1 * 2 * (h->NX - h->NP)); P_(w.imu_s, Np1 * 2 * (h->NX - h->NP)); }
         P_(w.al_mu, 1); P_(w.al_outer, 1); P_(w.al_viol, 1); P_(w.al_done, 1);
     }
 #undef P_

@@ -45,6 +45,9 @@ struct Work {
     // augmented Lagrangian
     double* lam;         // [N+1][2NU][Bp]
     double* imu;         // [N+1][2NU][Bp]
+    double* lam_s;       // [N+1][2NV][Bp]  multipliers / penalties of the velocity bounds (has_state_bounds)
+    double* imu_s;       // [N+1][2NV][Bp]
+    double* lxxv;        // [N+1][NV][Bp]   what the velocity bounds add to the diagonal of l_xx's velocity block
     double* al_mu;       // [Bp]
     int* al_outer;       // [Bp]
     double* al_viol;     // [Bp]
@@ -413,6 +416,21 @@ __global__ void __launch_bounds__(128) k_linearize(const Params prm, Work w) {
 
     double lx[NX], lxx[LR::LXX_LEN];
     double val = cost_expand<KIND>(prm, x, refrow, terminal, lx, lxx);
+    if (prm.has_state_bounds) {   // AL terms of the velocity bounds (every stage, the terminal one included)
+        constexpr int NV = NX - D::NP;
+        double lam[2 * NV], imu[2 * NV], lxa[NV], lxxa[NV];
+#pragma unroll
+        for (int j = 0; j < 2 * NV; ++j) {
+            lam[j] = w.lam_s[soa(stage, j, 2 * NV, Bp, b)];
+            imu[j] = w.imu_s[soa(stage, j, 2 * NV, Bp, b)];
+        }
+        val += al_box_terms<NV>(prm.xlb, prm.xub, x.xi, lam, imu, lxa, lxxa);
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            lx[D::NP + j] += lxa[j];
+            w.lxxv[soa(stage, j, NV, Bp, b)] = lxxa[j];
+        }
+    }
 
     if (!terminal) {
         double u[NU];

@@ -19,6 +19,19 @@ namespace trajopt {
 //            MS additionally accumulates the candidate's defect norm (:2565-2566)
 // Which problems run: `need` < 0 -> every running problem; otherwise those with ls_state == need.
 // ------------------------------------------------------------------------------------------
+// value of the AL terms of the velocity bounds at (stage, problem) for velocity xi
+template <int KIND>
+TO_DEV double al_state_value(const Params& prm, const Work& w, int stage, int Bp, int b, const double* xi) {
+    constexpr int NV = Dims<KIND>::NX - Dims<KIND>::NP;
+    double lam[2 * NV], imu[2 * NV], t1[NV], t2[NV];
+#pragma unroll
+    for (int j = 0; j < 2 * NV; ++j) {
+        lam[j] = w.lam_s[soa(stage, j, 2 * NV, Bp, b)];
+        imu[j] = w.imu_s[soa(stage, j, 2 * NV, Bp, b)];
+    }
+    return al_box_terms<NV>(prm.xlb, prm.xub, xi, lam, imu, t1, t2);
+}
+
 template <int KIND, bool MS, bool LINEAR, bool WRITE, bool COST>
 __global__ void __launch_bounds__(kBlock) k_forward(const Params prm, Work w, int a_lo, int a_cnt, int need,
                                                     int use_ls_state_as_alpha) {
@@ -82,6 +95,7 @@ __global__ void __launch_bounds__(kBlock) k_forward(const Params prm, Work w, in
                 }
                 c += al_terms<NU>(prm, unew, lam, imu, t1, t2);
             }
+            if (prm.has_state_bounds) c += al_state_value<KIND>(prm, w, i, Bp, b, xnew.xi);
             J = J + c;
         }
         load_state<KIND>(X, i + 1, Bp, b, xnext);
@@ -163,6 +177,7 @@ __global__ void __launch_bounds__(kBlock) k_forward(const Params prm, Work w, in
         double refrow[RefRow<KIND>::N];
         fetch_ref_row<KIND>(w, Bp, N, b, refrow);
         J = J + stage_cost<KIND>(prm, xnew, nullptr, refrow, true);
+        if (prm.has_state_bounds) J = J + al_state_value<KIND>(prm, w, N, Bp, b, xnew.xi);
         w.Jcand[(size_t)ai * Bp + b] = J;
         if (MS) w.Jcand[(size_t)(prm.n_alphas + ai) * Bp + b] = sqrt(dsq);
     }
@@ -531,19 +546,29 @@ static __global__ void k_ls_commit_ms(const Params prm, Work w, int it) {
 // ------------------------------------------------------------------------------------------
 template <int KIND>
 __global__ void k_al_update(const Params prm, Work w, double tol_constr, double mu_scale, double mu_max, int outer_it) {
-    constexpr int NU = Dims<KIND>::NU;
+    constexpr int NU = Dims<KIND>::NU, NS = Dims<KIND>::NS, NV = Dims<KIND>::NX - Dims<KIND>::NP, XI0 = NS - NV;
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     const int Bp = prm.Bp, N = prm.N;
     bool notdone = false;
     if (b < prm.B && !w.al_done[b]) {
         const double* U = w.U[w.sel[b]];
-        // max over stages of g (terminal row is zeros, :3245-3247)
+        const double* X = w.X[w.sel[b]];
+        // max over stages of g (the input rows of the terminal stage are zeros, :3245-3247)
         double gmax = 0.0;
         for (int i = 0; i < N; ++i) {
 #pragma unroll
             for (int j = 0; j < NU; ++j) {
                 const double u = U[soa(i, j, NU, Bp, b)];
                 gmax = fmax(gmax, fmax(prm.lb[j] - u, u - prm.ub[j]));
+            }
+        }
+        if (prm.has_state_bounds) {
+            for (int i = 0; i <= N; ++i) {
+#pragma unroll
+                for (int j = 0; j < NV; ++j) {
+                    const double v = X[soa(i, XI0 + j, NS, Bp, b)];
+                    gmax = fmax(gmax, fmax(prm.xlb[j] - v, v - prm.xub[j]));
+                }
             }
         }
         w.al_viol[b] = gmax;
@@ -570,6 +595,22 @@ __global__ void k_al_update(const Params prm, Work w, double tol_constr, double 
             // terminal row: g = 0 -> lambda stays 0, Imu = mu_new (no effect on the cost)
 #pragma unroll
             for (int j = 0; j < 2 * NU; ++j) w.imu[soa(N, j, 2 * NU, Bp, b)] = mu_new;
+            if (prm.has_state_bounds) {
+                for (int i = 0; i <= N; ++i) {
+#pragma unroll
+                    for (int j = 0; j < NV; ++j) {
+                        const double v = X[soa(i, XI0 + j, NS, Bp, b)];
+                        const double g[2] = {prm.xlb[j] - v, v - prm.xub[j]};
+#pragma unroll
+                        for (int s = 0; s < 2; ++s) {
+                            const size_t idx = soa(i, s * NV + j, 2 * NV, Bp, b);
+                            const double ln = fmax(0.0, w.lam_s[idx] + w.imu_s[idx] * g[s]);
+                            w.lam_s[idx] = ln;
+                            w.imu_s[idx] = (g[s] < 0.0 && ln == 0.0) ? 0.0 : mu_new;
+                        }
+                    }
+                }
+            }
             w.al_mu[b] = mu_new;
         }
     }
@@ -587,6 +628,14 @@ __global__ void k_al_init(const Params prm, Work w, double mu0) {
     for (int j = 0; j < 2 * NU; ++j) {
         w.lam[soa(stage, j, 2 * NU, prm.Bp, b)] = 0.0;
         w.imu[soa(stage, j, 2 * NU, prm.Bp, b)] = mu0;
+    }
+    if (prm.has_state_bounds) {
+        constexpr int NV = Dims<KIND>::NX - Dims<KIND>::NP;
+#pragma unroll
+        for (int j = 0; j < 2 * NV; ++j) {
+            w.lam_s[soa(stage, j, 2 * NV, prm.Bp, b)] = 0.0;
+            w.imu_s[soa(stage, j, 2 * NV, prm.Bp, b)] = mu0;
+        }
     }
     if (stage == 0) {
         w.al_mu[b] = mu0;

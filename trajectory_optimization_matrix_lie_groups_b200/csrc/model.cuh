@@ -174,27 +174,32 @@ TO_DEV void tracking_error(const State<KIND>& x, const double* __restrict__ refr
 
 // AL terms of InputConstraint g = [lb - u; u - ub] with multipliers lam[2NU], penalties imu[2NU]
 //   value: lam^T g + 1/2 g^T Imu g ;  l_u += g_u^T (lam + Imu g) ;  l_uu += g_u^T Imu g_u (diagonal)
-template <int NU>
-TO_DEV double al_terms(const Params& prm, const double* u, const double* lam, const double* imu, double* lu_add, double* luu_add) {
+template <int M>
+TO_DEV double al_box_terms(const double* lb, const double* ub, const double* v, const double* lam, const double* imu,
+                           double* l_add, double* ll_add) {
     double val = 0.0;
 #pragma unroll
-    for (int j = 0; j < NU; ++j) {
-        const double g0 = prm.lb[j] - u[j];
-        const double g1 = u[j] - prm.ub[j];
-        val += lam[j] * g0 + lam[NU + j] * g1;
+    for (int j = 0; j < M; ++j) {
+        const double g0 = lb[j] - v[j];
+        const double g1 = v[j] - ub[j];
+        val += lam[j] * g0 + lam[M + j] * g1;
         const double t0 = lam[j] + imu[j] * g0;
-        const double t1 = lam[NU + j] + imu[NU + j] * g1;
-        lu_add[j] = t1 - t0;
-        luu_add[j] = imu[j] + imu[NU + j];
+        const double t1 = lam[M + j] + imu[M + j] * g1;
+        l_add[j] = t1 - t0;
+        ll_add[j] = imu[j] + imu[M + j];
     }
     double quad = 0.0;
 #pragma unroll
-    for (int j = 0; j < NU; ++j) {
-        const double g0 = prm.lb[j] - u[j];
-        const double g1 = u[j] - prm.ub[j];
-        quad += g0 * imu[j] * g0 + g1 * imu[NU + j] * g1;
+    for (int j = 0; j < M; ++j) {
+        const double g0 = lb[j] - v[j];
+        const double g1 = v[j] - ub[j];
+        quad += g0 * imu[j] * g0 + g1 * imu[M + j] * g1;
     }
     return val + 0.5 * quad;
+}
+template <int NU>
+TO_DEV double al_terms(const Params& prm, const double* u, const double* lam, const double* imu, double* lu_add, double* luu_add) {
+    return al_box_terms<NU>(prm.lb, prm.ub, u, lam, imu, lu_add, luu_add);
 }
 
 // Stage cost value only (forward passes):  e^T W1 e + dxi^T W2 dxi (+ u^T R u)

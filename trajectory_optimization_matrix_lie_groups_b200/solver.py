@@ -64,7 +64,7 @@ class BatchSolver:
     def set_params(self, *, dt, Ib, mass, Q, R, P, gravity=9.8, max_iters=100, tol_grad_norm=1e-6,
                    tol_d_norm=1e-6, max_reg=1e10, rollout="nonlinear", line_search=False, n_alphas=0,
                    defect_kappa=0.0, lb=None, ub=None, n_al_iters=100, al_mu0=1e-2, al_mu_scale=10.0,
-                   al_mu_max=1e8, tol_constr=1e-2, length=0.0):
+                   al_mu_max=1e8, tol_constr=1e-2, length=0.0, xi_lb=None, xi_ub=None):
         NX, NU = self.NX, self.NU
         p = _lib.Params()
         p.dt = float(dt)
@@ -72,6 +72,14 @@ class BatchSolver:
         p.mass = float(mass)
         p.gravity = float(gravity)
         p.length = float(length)
+        p.has_state_bounds = int(xi_lb is not None)
+        if xi_lb is not None:
+            nv = self.NX - self.NP
+            xl = np.broadcast_to(np.asarray(xi_lb, dtype=np.float64), (nv,))
+            xu = np.broadcast_to(np.asarray(xi_ub, dtype=np.float64), (nv,))
+            for i in range(nv):
+                p.xi_lb[i], p.xi_ub[i] = xl[i], xu[i]
+        self._has_state_bounds = xi_lb is not None
         for name, M, n in (("Q", Q, NX), ("P", P, NX), ("R", R, NU)):
             M = np.asarray(M, dtype=np.float64)
             if M.shape != (n, n):
@@ -181,6 +189,10 @@ class BatchSolver:
                "outer_iters": self._new(B, dtype=torch.int32), "violation": self._new(B)}
         check(lib.trajopt_export_al(self._h, _ptr(out["lmbd"]), _ptr(out["imu"]), _ptr(out["mu"]),
                                     _ptr(out["outer_iters"]), _ptr(out["violation"]), _stream(self.device)))
+        if getattr(self, "_has_state_bounds", False):
+            cs = 2 * (self.NX - self.NP)
+            out["lmbd_state"], out["imu_state"] = self._new(B, N + 1, cs), self._new(B, N + 1, cs)
+            check(lib.trajopt_export_al_state(self._h, _ptr(out["lmbd_state"]), _ptr(out["imu_state"]), _stream(self.device)))
         return out
 
     def solve(self, x0, us_init=None, trajectories=True):

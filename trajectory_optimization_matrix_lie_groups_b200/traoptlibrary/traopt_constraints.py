@@ -63,3 +63,37 @@ class InputConstraint(BaseConstraint):
         if terminal:
             return np.zeros((self._constr_size, self._action_size))
         return np.vstack((-np.identity(self._action_size), np.identity(self._action_size)))
+
+
+class InputVelocityConstraint(InputConstraint):
+    """Box bounds on the input AND on the body velocity xi = [omega, v] — an addition to the reference (which only has
+    `InputConstraint`), with the same BaseConstraint interface: g = [lb_u - u; u - ub_u; lb_xi - xi; xi - ub_xi].
+    The velocity rows stay active at the terminal stage."""
+
+    def __init__(self, input_lb, input_ub, xi_lb, xi_ub, state_size=(6, 6), action_size=6):
+        super().__init__(input_lb, input_ub, state_size, action_size)
+        self._nv = state_size[1]
+        self._xlb = np.broadcast_to(np.asarray(xi_lb, dtype=float), (self._nv,)).copy()
+        self._xub = np.broadcast_to(np.asarray(xi_ub, dtype=float), (self._nv,)).copy()
+        self._constr_size = 2 * action_size + 2 * self._nv
+
+    xi_lb = property(lambda self: self._xlb)
+    xi_ub = property(lambda self: self._xub)
+
+    def g(self, x, u, i, terminal=False):
+        xi = np.asarray(x[1], dtype=float).reshape(self._nv)
+        gu = np.zeros(2 * self._action_size) if terminal else super().g(x, u, i)
+        return np.concatenate((gu, self._xlb - xi, xi - self._xub))
+
+    def g_x(self, x, u, i, terminal=False):
+        G = np.zeros((self._constr_size, self._state_size))
+        m2, nv, npose = 2 * self._action_size, self._nv, self._state_size - self._nv
+        G[m2:m2 + nv, npose:] = -np.identity(nv)
+        G[m2 + nv:, npose:] = np.identity(nv)
+        return G
+
+    def g_u(self, x, u, i, terminal=False):
+        G = np.zeros((self._constr_size, self._action_size))
+        if not terminal:
+            G[:2 * self._action_size] = super().g_u(x, u, i)
+        return G

@@ -114,6 +114,8 @@ class _NativeController(BaseController):
         bounds = None
         if self.METHOD == "al_ms":
             bounds = (self.constr.input_lb, self.constr.input_ub)
+            if hasattr(self.constr, "xi_lb"):
+                params = dict(params, xi_lb=self.constr.xi_lb, xi_ub=self.constr.xi_ub)
         if s is None:
             s = _native.make_solver(self._kind, self.METHOD, self.N, B, self.dynamics, cost, self._q_ref, self._xi_ref,
                                     device=device, bounds=bounds, **params)
@@ -411,8 +413,16 @@ class AL_iLQR_Tracking_SE3_MS(_NativeController):
             active = s.iterate(1)
             out = s.export()
             us = out["us"][0].cpu().numpy()
-            constr_eval = np.vstack([np.concatenate((self.constr.input_lb - u, u - self.constr.input_ub)) for u in us]
-                                    + [np.zeros(c)])
+            if hasattr(self.constr, "xi_lb"):
+                xs_it = _native.rows_states(kind, out["xs"][0].cpu().numpy())
+                constr_eval = np.vstack([self.constr.g(xs_it[i], us[i], i) for i in range(self.N)]
+                                        + [self.constr.g(xs_it[self.N], None, self.N, terminal=True)])
+                lmbd = np.concatenate((lmbd, al["lmbd_state"][0].cpu().numpy()), axis=1)
+                Imu = np.stack([np.diag(np.concatenate((np.diag(Imu[i]), r))) for i, r in
+                                enumerate(al["imu_state"][0].cpu().numpy())])
+            else:
+                constr_eval = np.vstack([np.concatenate((self.constr.input_lb - u, u - self.constr.input_ub)) for u in us]
+                                        + [np.zeros(c)])
             converged = bool(np.max(constr_eval) < tol_constr)
             self.al.lmbd, self.al.Imu, self.al.mu = lmbd, Imu, mu
             if on_iteration_al:
