@@ -112,6 +112,11 @@ int trajopt_set_reference(trajopt_handle* h, const double* h_q_ref, const double
  * (traopt_cost.py:614-616) of problem b then use reference b. */
 int trajopt_set_reference_batch(trajopt_handle* h, const double* d_q_ref, const double* d_xi_ref, void* stream);
 
+/* One horizon per problem: DEVICE pointer d_N [B], clamped to [1, N]; NULL restores N for every problem.  Problem b
+ * then is the N_b-stage problem on the first N_b + 1 rows of its reference (terminal cost at stage N_b); rows of the
+ * exported trajectories beyond N_b hold the initial guess.  Set before trajopt_begin. */
+int trajopt_set_horizons(trajopt_handle* h, const int32_t* d_N, void* stream);
+
 /* us_mode: 0 = zeros (d_us_init ignored), 1 = one [N][NU] path shared by the batch, 2 = [B][N][NU] */
 int trajopt_begin(trajopt_handle* h, const double* d_x0, const double* d_us_init, int us_mode, void* stream);
 /* run up to n_iters more iterations; *n_active_out (may be NULL) = problems still running afterwards */

@@ -90,6 +90,7 @@ int trajopt_create(int kind, int method, int N, int B, int device, trajopt_handl
     A_(w.x0, (size_t)h->NS * Bp);
     A_(w.counters, 4);
     A_(w.orig, Bp);
+    A_(w.Nb, Bp);
     A_(h->d_dweight, Bp);
     if (method == TRAJOPT_AL_MS) {
         A_(w.lam, Np1 * 2 * h->NU * Bp); A_(w.imu, Np1 * 2 * h->NU * Bp);
@@ -105,6 +106,8 @@ int trajopt_create(int kind, int method, int N, int B, int device, trajopt_handl
         trajopt_destroy(h);
         return rc;
     }
+    LAUNCH(k_set_horizons, blocks_for(h->Bp, 128), 128, 0, (cudaStream_t)0, h->B, h->Bp, h->N, (const int*)nullptr, h->w.Nb);
+    CUDA_OK(cudaDeviceSynchronize());
     *out = h;
     return 0;
 }
@@ -252,6 +255,15 @@ int trajopt_set_reference_batch(trajopt_handle* h, const double* d_q_ref, const 
     if (rc) return rc;
     h->w.ref_batch = h->d_ref_batch;
     h->have_ref = true;
+    h->begun = false;
+    return 0;
+}
+
+int trajopt_set_horizons(trajopt_handle* h, const int32_t* d_N, void* stream) {
+    if (!h) return fail(TRAJOPT_E_INVALID, "trajopt_set_horizons: NULL handle");
+    DeviceGuard guard(h->device);
+    LAUNCH(k_set_horizons, blocks_for(h->Bp, 128), 128, 0, (cudaStream_t)stream, h->B, h->Bp, h->N, (const int*)d_N, h->w.Nb);
+    h->var_horizons = d_N != nullptr;
     h->begun = false;
     return 0;
 }

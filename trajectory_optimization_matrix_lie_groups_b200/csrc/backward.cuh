@@ -99,7 +99,8 @@ __global__ void __launch_bounds__(LPW) k_backward(const Params prm, Work w, int 
     const int lane = threadIdx.x;
     const int b = blockIdx.x * LPW + lane;
     if (b >= prm.B || w.status[b] != TRAJOPT_RUNNING) return;
-    const int N = prm.N;
+    const int N = prm.N;                 // record layout stride; the problem's own horizon is Nb
+    const int Nb = w.Nb[b];
     const size_t Bp = (size_t)prm.Bp;
     double* Vs = sm + lane;
     double* Vn = sm + NT * LPW + lane;
@@ -112,16 +113,16 @@ __global__ void __launch_bounds__(LPW) k_backward(const Params prm, Work w, int 
     if constexpr (MS) {
         // J_new of the previous iteration: Python sum, left to right, + terminal (:2742-2754)
         double s = 0.0;
-        for (int i = 0; i < N; ++i) s += w.Lc[(size_t)i * Bp + b];
-        Jcur = s + w.Lc[(size_t)N * Bp + b];
+        for (int i = 0; i < Nb; ++i) s += w.Lc[(size_t)i * Bp + b];
+        Jcur = s + w.Lc[(size_t)Nb * Bp + b];
         double q = 0.0;
-        for (int i = 0; i < N; ++i) q += w.Dsq[(size_t)i * Bp + b];
+        for (int i = 0; i < Nb; ++i) q += w.Dsq[(size_t)i * Bp + b];
         dn = sqrt(q);
         w.dnorm[b] = dn;
         if (it > 0) w.Jhist[(size_t)(it - 1) * Bp + b] = Jcur;
         w.defhist[(size_t)it * Bp + b] = dn;
     } else {
-        Jcur = pairwise_sum(w.Lc + b, Bp, N + 1);      // J_opt = L.sum() (:1935)
+        Jcur = pairwise_sum(w.Lc + b, Bp, Nb + 1);     // J_opt = L.sum() (:1935)
     }
     w.J[b] = Jcur;
     if (!isfinite(Jcur)) {
@@ -135,7 +136,7 @@ __global__ void __launch_bounds__(LPW) k_backward(const Params prm, Work w, int 
 
     // ---- terminal condition: V_x = l_x(N), V_xx = l_xx(N) --------------------------------
     {
-        const double* rec = lin + lsoa(N, 0, F, N + 1, b);
+        const double* rec = lin + lsoa(Nb, 0, F, N + 1, b);
 #pragma unroll
         for (int j = 0; j < NX; ++j) Vxs[j * LPW] = rec[(size_t)(LR::LX_OFF + j) * kRecStride];
 #pragma unroll
@@ -144,7 +145,7 @@ __global__ void __launch_bounds__(LPW) k_backward(const Params prm, Work w, int 
             for (int c = r; c < NX; ++c) {
                 double v;
                 if (c < NP) v = rec[(size_t)(LR::LXX_OFF + tri_idx(NP, r, c)) * kRecStride];
-                else if (r >= NP) v = 2.0 * prm.P2[(r - NP) * NV + (c - NP)] + ((r == c && prm.has_state_bounds) ? w.lxxv[soa(N, r - NP, NV, (int)Bp, b)] : 0.0);
+                else if (r >= NP) v = 2.0 * prm.P2[(r - NP) * NV + (c - NP)] + ((r == c && prm.has_state_bounds) ? w.lxxv[soa(Nb, r - NP, NV, (int)Bp, b)] : 0.0);
                 else v = 0.0;
                 Vs[tri_idx(NX, r, c) * LPW] = v;
             }
@@ -160,6 +161,7 @@ __global__ void __launch_bounds__(LPW) k_backward(const Params prm, Work w, int 
     int flags = 0;
 
     for (int i = N - 1; i >= 0; --i) {
+        if (i >= Nb) continue;           // stages beyond this problem's horizon
         const double* __restrict__ rec = lin + lsoa(i, 0, F, N + 1, b);
         const BvStage<KIND> Bv(prm, rec, kRecStride);   // velocity rows of f_u: constant, or per stage (pendulum)
         if (i > 0) {   // pull the next record towards L2 while this stage computes
@@ -508,7 +510,7 @@ __global__ void __launch_bounds__(LPW) k_backward(const Params prm, Work w, int 
 
     w.mu[b] = mu;
     w.delta[b] = delta;
-    const double g = gsum / (double)N;
+    const double g = gsum / (double)Nb;
     w.grad[b] = g;
     w.gradhist[(size_t)it * Bp + b] = g;
     int st = TRAJOPT_RUNNING;

@@ -34,6 +34,7 @@ struct trajopt_handle {
     Work w{};
     trajopt_params user{};
     bool have_params = false, have_ref = false, begun = false;
+    bool var_horizons = false;   // trajopt_set_horizons was given a non-NULL array
     int it = 0;              // next inner iteration
     bool inner_done = true;  // the inner loop of the current fit() / AL outer iteration has ended
     int al_outer = 0;        // AL outer iterations completed
@@ -157,8 +158,13 @@ int run_backward(trajopt_handle* h, cudaStream_t s, int it) {
     if constexpr (!on_so3(KIND)) {
         if (!use_one_warp_sweep()) {
             constexpr size_t smem3 = B3Smem<KIND>::BYTES;
-            CUDA_OK(cudaFuncSetAttribute(k_backward3<KIND, MS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
-            LAUNCH((k_backward3<KIND, MS>), h->Bp / 32, kB3Threads, smem3, s, h->prm, h->w, it);
+            if (h->var_horizons) {
+                CUDA_OK(cudaFuncSetAttribute(k_backward3<KIND, MS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+                LAUNCH((k_backward3<KIND, MS, true>), h->Bp / 32, kB3Threads, smem3, s, h->prm, h->w, it);
+            } else {
+                CUDA_OK(cudaFuncSetAttribute(k_backward3<KIND, MS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+                LAUNCH((k_backward3<KIND, MS, false>), h->Bp / 32, kB3Threads, smem3, s, h->prm, h->w, it);
+            }
             return 0;
         }
     }
@@ -296,7 +302,7 @@ inline int maybe_compact(trajopt_handle* h, cudaStream_t s, int act) {
     int rc = 0;
 #define P_(ptr, rows) if (!rc) rc = permute_array(h, s, (ptr), (size_t)(rows), front)
     P_(w.X[0], Np1 * h->NS); P_(w.X[1], Np1 * h->NS); P_(w.U[0], N * h->NU); P_(w.U[1], N * h->NU);
-    P_(w.x0, h->NS); P_(w.sel, 1); P_(w.orig, 1);
+    P_(w.x0, h->NS); P_(w.sel, 1); P_(w.orig, 1); P_(w.Nb, 1);
     P_(w.J, 1); P_(w.grad, 1); P_(w.dnorm, 1); P_(w.mu, 1); P_(w.delta, 1);
     P_(w.iters, 1); P_(w.status, 1); P_(w.ls_state, 1);
     P_(w.Jhist, mi); P_(w.gradhist, mi + 1); P_(w.defhist, mi + 1); P_(w.alphahist, mi);

@@ -53,6 +53,7 @@ struct Work {
     double* al_viol;     // [Bp]
     int* al_done;        // [Bp]
     int* counters;       // [0] running problems, [1] pending line searches, [2] AL problems not converged
+    int* Nb;             // [Bp] horizon of each problem, 1 <= Nb <= N (trajopt_set_horizons; default N for all)
     int* orig;           // [Bp] slot -> problem index of the caller (identity until a compaction moves problems)
 };
 
@@ -393,6 +394,8 @@ __global__ void __launch_bounds__(128) k_linearize(const Params prm, Work w) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     const int stage = blockIdx.y;
     if (b >= prm.B || w.status[b] != TRAJOPT_RUNNING) return;
+    const int Nb = w.Nb[b];
+    if (stage > Nb) return;                  // beyond this problem's horizon
     const int Bp = prm.Bp;
     const double* X = w.X[w.sel[b]];
     const double* U = w.U[w.sel[b]];
@@ -412,7 +415,7 @@ __global__ void __launch_bounds__(128) k_linearize(const Params prm, Work w) {
 
     State<KIND> x;
     load_state<KIND>(X, stage, Bp, b, x);
-    const bool terminal = (stage == prm.N);
+    const bool terminal = (stage == Nb);
 
     double lx[NX], lxx[LR::LXX_LEN];
     double val = cost_expand<KIND>(prm, x, refrow, terminal, lx, lxx);

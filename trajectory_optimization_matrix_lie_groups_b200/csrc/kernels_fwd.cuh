@@ -64,8 +64,9 @@ __global__ void __launch_bounds__(kBlock) k_forward(const Params prm, Work w, in
     xnew = x;
     if (WRITE) store_state<KIND>(Xn, 0, Bp, b, xnew);
     double J = 0.0, dsq = 0.0;
+    const int Nb = w.Nb[b];              // this problem's horizon (<= N)
 
-    for (int i = 0; i < N; ++i) {
+    for (int i = 0; i < Nb; ++i) {
         double refrow[RefRow<KIND>::N];
         if (COST) fetch_ref_row<KIND>(w, Bp, i, b, refrow);
         double dx[NX];
@@ -175,9 +176,9 @@ __global__ void __launch_bounds__(kBlock) k_forward(const Params prm, Work w, in
     }
     if (COST) {
         double refrow[RefRow<KIND>::N];
-        fetch_ref_row<KIND>(w, Bp, N, b, refrow);
+        fetch_ref_row<KIND>(w, Bp, Nb, b, refrow);
         J = J + stage_cost<KIND>(prm, xnew, nullptr, refrow, true);
-        if (prm.has_state_bounds) J = J + al_state_value<KIND>(prm, w, N, Bp, b, xnew.xi);
+        if (prm.has_state_bounds) J = J + al_state_value<KIND>(prm, w, Nb, Bp, b, xnew.xi);
         w.Jcand[(size_t)ai * Bp + b] = J;
         if (MS) w.Jcand[(size_t)(prm.n_alphas + ai) * Bp + b] = sqrt(dsq);
     }
@@ -259,8 +260,10 @@ __global__ void __launch_bounds__(kBlock) k_forward_ms_full(const Params prm, Wo
     xnew = x;
     if (act) store_state<KIND>(Xn, 0, Bp, b, xnew);
     uint32_t ph0 = 0, ph1 = 0;
+    const int Nb = w.Nb[b];              // this problem's horizon; the staging below runs over the group's N stages
     for (int i = 0; i < N; ++i) {
         const int buf = i & 1;
+        const bool live = act && (i < Nb);
         // independent of the recursion: issue these loads first
         load_state<KIND>(X, i + 1, Bp, b, xnext);
         double G[GP], fxi[NV], dxi[NV];
@@ -289,7 +292,7 @@ __global__ void __launch_bounds__(kBlock) k_forward_ms_full(const Params prm, Wo
         }
         __syncwarp();                       // every lane is done with this buffer
         if (i + 2 < N) issue(i + 2, buf);
-        if (act) {
+        if (live) {
 #pragma unroll
             for (int a = 0; a < NU; ++a) Un[soa(i, a, NU, Bp, b)] = unew[a];
         }
@@ -302,7 +305,7 @@ __global__ void __launch_bounds__(kBlock) k_forward_ms_full(const Params prm, Wo
         }
 #pragma unroll
         for (int j = 0; j < NV; ++j) xn1.xi[j] = xnext.xi[j] + fnew.xi[j] - fxi[j] + dxi[j];
-        if (act) store_state<KIND>(Xn, i + 1, Bp, b, xn1);
+        if (live) store_state<KIND>(Xn, i + 1, Bp, b, xn1);
         xnew = xn1;
         x = xnext;
     }
@@ -385,6 +388,7 @@ __global__ void __launch_bounds__(kBlock) k_ms_expected(const Params prm, Work w
     const int b = blockIdx.x * kBlock + threadIdx.x;
     const int Bp = prm.Bp, N = prm.N;
     if (b >= prm.B || w.status[b] != TRAJOPT_RUNNING) return;
+    const int Nb = w.Nb[b];
     const double* lin = w.lin;
     const int cur = w.sel[b];
     const double* U = w.U[cur];
@@ -396,7 +400,7 @@ __global__ void __launch_bounds__(kBlock) k_ms_expected(const Params prm, Work w
 #pragma unroll
     for (int j = 0; j < NX; ++j) dx[j] = 0.0;
     double c1 = 0.0, c2 = 0.0;
-    for (int i = 0; i < N; ++i) {
+    for (int i = 0; i < Nb; ++i) {
         double du[NU];
 #pragma unroll
         for (int a = 0; a < NU; ++a) {
@@ -466,12 +470,12 @@ __global__ void __launch_bounds__(kBlock) k_ms_expected(const Params prm, Work w
     {
         double f1 = 0.0, f2 = 0.0;
 #pragma unroll
-        for (int c = 0; c < NX; ++c) f1 += lin[lsoa(N, LR::LX_OFF + c, F, N + 1, b)] * dx[c];
+        for (int c = 0; c < NX; ++c) f1 += lin[lsoa(Nb, LR::LX_OFF + c, F, N + 1, b)] * dx[c];
 #pragma unroll
         for (int r = 0; r < NP; ++r)
 #pragma unroll
             for (int c = 0; c < NP; ++c)
-                f2 += dx[r] * lin[lsoa(N, LR::LXX_OFF + sym_idx(NP, r, c), F, N + 1, b)] * dx[c];
+                f2 += dx[r] * lin[lsoa(Nb, LR::LXX_OFF + sym_idx(NP, r, c), F, N + 1, b)] * dx[c];
 #pragma unroll
         for (int r = 0; r < NV; ++r)
 #pragma unroll
@@ -489,7 +493,7 @@ __global__ void __launch_bounds__(kBlock) k_ms_expected(const Params prm, Work w
     w.Jcand[base + Bp] = c2;
     w.Jcand[base + 2 * (size_t)Bp] = dw;
     // merit uses J_opt = L.sum() (pairwise, :2507) of the current trajectory
-    w.Jcand[base + 3 * (size_t)Bp] = pairwise_sum(w.Lc + b, (size_t)Bp, N + 1) + dw * dn;
+    w.Jcand[base + 3 * (size_t)Bp] = pairwise_sum(w.Lc + b, (size_t)Bp, Nb + 1) + dw * dn;
 }
 
 // accept the first alpha with merit_new - merit < gamma (dJ_exp(alpha) - alpha w ||d||) (:2576)
@@ -548,9 +552,10 @@ template <int KIND>
 __global__ void k_al_update(const Params prm, Work w, double tol_constr, double mu_scale, double mu_max, int outer_it) {
     constexpr int NU = Dims<KIND>::NU, NS = Dims<KIND>::NS, NV = Dims<KIND>::NX - Dims<KIND>::NP, XI0 = NS - NV;
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    const int Bp = prm.Bp, N = prm.N;
+    const int Bp = prm.Bp;
     bool notdone = false;
     if (b < prm.B && !w.al_done[b]) {
+        const int N = w.Nb[b];          // this problem's horizon
         const double* U = w.U[w.sel[b]];
         const double* X = w.X[w.sel[b]];
         // max over stages of g (the input rows of the terminal stage are zeros, :3245-3247)
@@ -685,6 +690,14 @@ __global__ void k_permute_scatter(int rows, int Bp, int front, T* __restrict__ d
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= front) return;
     for (int r = blockIdx.y; r < rows; r += gridDim.y) data[(size_t)r * Bp + n] = scratch[(size_t)r * front + n];
+}
+// per-problem horizons: out[b] = clamp(in[b], 1, N) for b < B (in == NULL: N), N for the padding slots
+static __global__ void k_set_horizons(int B, int Bp, int N, const int* __restrict__ in, int* __restrict__ out) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= Bp) return;
+    int v = N;
+    if (in && b < B) v = min(max(in[b], 1), N);
+    out[b] = v;
 }
 static __global__ void k_identity(int n, int* out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -126,6 +126,15 @@ class BatchSolver:
         check(lib.trajopt_set_reference_batch(self._h, _ptr(q), _ptr(xi), _stream(self.device)))
         torch.cuda.current_stream(self.device).synchronize()      # q, xi may be temporaries
 
+    def set_horizons(self, horizons=None):
+        """One horizon per problem, (B,) ints in [1, N]; None restores N for all."""
+        if horizons is None:
+            check(lib.trajopt_set_horizons(self._h, C.c_void_p(0), _stream(self.device)))
+            return
+        t = self._dev(np.asarray(horizons, dtype=np.int32), (self.B,), dtype=torch.int32)
+        check(lib.trajopt_set_horizons(self._h, _ptr(t), _stream(self.device)))
+        torch.cuda.current_stream(self.device).synchronize()
+
     # ------------------------------------------------------------------------------------ solving
     def _dev(self, a, shape=None, dtype=torch.float64):
         t = torch.as_tensor(a, dtype=dtype)
