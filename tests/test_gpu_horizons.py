@@ -59,3 +59,23 @@ def test_default_horizons_unchanged_and_reset():
     assert np.array_equal(a[[0, 1, 3]], b[[0, 1, 3]]) and not np.array_equal(a[2, :10], b[2, :10])
     s.set_horizons(None)
     assert np.array_equal(s.solve(X0)["us"].cpu().numpy(), a)
+
+
+def test_fit_batch_horizons_match_single_problem_fits():
+    """Mirror class API: fit_batch(horizons=...) against `fit` of a controller built with that horizon."""
+    from trajectory_optimization_matrix_lie_groups_b200.traoptlibrary import traopt_controller as tc, traopt_cost, traopt_dynamics
+    g = problems.load_golden("se3_n120")
+    N = 40
+    q, xi = g["prob_q_ref"][:N + 1], g["prob_xi_ref"][:N + 1]
+    dyn = traopt_dynamics.SE3Dynamics(g["prob_J"], float(g["prob_dt"]))
+    cost = traopt_cost.SE3TrackingQuadraticGaussNewtonCost(g["prob_Q"], g["prob_R"], g["prob_P"], q, xi)
+    ctrl = tc.iLQR_Tracking_SE3_MS(dyn, cost, N, q, xi, rollout="nonlinear")
+    x0 = [g["prob_x0_q"], np.asarray(g["prob_x0_xi"], dtype=float).reshape(-1)]
+    horizons = [40, 9, 25]
+    res = ctrl.fit_batch([x0] * 3, n_iterations=60, tol_grad_norm=1e-10, horizons=horizons)
+    assert np.all(res.converged)
+    for b, Nb in enumerate(horizons):
+        cost_b = traopt_cost.SE3TrackingQuadraticGaussNewtonCost(g["prob_Q"], g["prob_R"], g["prob_P"], q[:Nb + 1], xi[:Nb + 1])
+        ctrl_b = tc.iLQR_Tracking_SE3_MS(dyn, cost_b, Nb, q[:Nb + 1], xi[:Nb + 1], rollout="nonlinear")
+        xs, us, *_ = ctrl_b.fit(x0, np.zeros((Nb, 6)), n_iterations=60, tol_grad_norm=1e-10)
+        assert np.max(np.abs(us - res.us[b][:Nb])) < 1e-9

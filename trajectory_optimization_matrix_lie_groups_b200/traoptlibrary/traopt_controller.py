@@ -153,13 +153,14 @@ class _NativeController(BaseController):
     # -------------------------------------------------------------------------------- fit_batch
     def fit_batch(self, x0_batch, us_init=None, n_iterations=100, tol_grad_norm=None, tol_d_norm=1e-6,
                   return_trajectories=True, return_hist=False, device=None, shard=None, q_ref_batch=None,
-                  xi_ref_batch=None, **extra):
+                  xi_ref_batch=None, horizons=None, **extra):
         """Solve B problems that differ in their initial state (and optionally initial controls).
 
         x0_batch: list of reference-style states [q, xi], or an array of device rows (B, NS).
         us_init:  None (zeros), (N, m) shared, or (B, N, m).
         q_ref_batch, xi_ref_batch: one reference per problem — (B, N+1, 4, 4) poses (or (B, N+1, 3, 3) / device rows)
                   and (B, N+1, 6|3) twists; default: the controller's own reference for every problem.
+        horizons: (B,) ints, 1 <= N_b <= N: problem b is solved over its first N_b stages (terminal cost at N_b).
         shard:    split the batch over the ranks of the initialised torch.distributed job
                   (default: yes when a job is initialised); summaries are all-gathered, trajectories
                   stay on the rank that solved them.
@@ -187,6 +188,7 @@ class _NativeController(BaseController):
                 sv.set_reference_batch(q_rows, np.asarray(xi_ref_batch, dtype=float)[lo_:lo_ + b, :self.N + 1])
             else:
                 sv.set_reference(_native.ref_rows(self._kind, self._q_ref)[:self.N + 1], self._xi_ref_array()[:self.N + 1])
+            sv.set_horizons(None if horizons is None else np.asarray(horizons)[lo_:lo_ + b])
             return sv
         if shard and ws > 1:
             lo, hi = _dist.shard_bounds(B, rank, ws)
