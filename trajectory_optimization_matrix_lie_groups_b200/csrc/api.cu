@@ -102,6 +102,14 @@ int trajopt_create(int kind, int method, int N, int B, int device, trajopt_handl
     if (!rc && cudaMallocHost((void**)&h->h_counters, 4 * sizeof(int)) != cudaSuccess) rc = fail(TRAJOPT_E_CUDA, "cudaMallocHost failed");
     if (!rc && (cudaEventCreate(&h->ev[0]) != cudaSuccess || cudaEventCreate(&h->ev[1]) != cudaSuccess))
         rc = fail(TRAJOPT_E_CUDA, "cudaEventCreate failed");
+    if (!rc && method != TRAJOPT_SS) {
+        int pr_least = 0, pr_greatest = 0;
+        cudaDeviceGetStreamPriorityRange(&pr_least, &pr_greatest);
+        if (cudaStreamCreateWithPriority(&h->s2, cudaStreamNonBlocking, pr_greatest) != cudaSuccess) rc = fail(TRAJOPT_E_CUDA, "cudaStreamCreate failed");
+        for (int c = 0; c < kMaxChunks && !rc; ++c)
+            if (cudaEventCreateWithFlags(&h->ev_chunk[c], cudaEventDisableTiming) != cudaSuccess) rc = fail(TRAJOPT_E_CUDA, "cudaEventCreate failed");
+        if (!rc && cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) rc = fail(TRAJOPT_E_CUDA, "cudaEventCreate failed");
+    }
     if (rc) {
         trajopt_destroy(h);
         return rc;
@@ -124,6 +132,9 @@ int trajopt_destroy(trajopt_handle* h) {
     if (h->h_counters) cudaFreeHost(h->h_counters);
     if (h->ev[0]) cudaEventDestroy(h->ev[0]);
     if (h->ev[1]) cudaEventDestroy(h->ev[1]);
+    for (cudaEvent_t e : h->ev_chunk) if (e) cudaEventDestroy(e);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->s2) cudaStreamDestroy(h->s2);
     delete h;
     return 0;
 }

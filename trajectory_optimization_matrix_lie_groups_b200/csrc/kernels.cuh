@@ -387,18 +387,19 @@ __global__ void __launch_bounds__(kBlock) k_init_ss(const Params prm, Work w) {
 // ------------------------------------------------------------------------------------------
 // REFB: per-problem references (a separate instantiation keeps the shared-reference kernel's register budget intact)
 template <int KIND, bool MS, bool REFB>
-__global__ void __launch_bounds__(128) k_linearize(const Params prm, Work w) {
+__global__ void __launch_bounds__(128) k_linearize(const Params prm, Work w, int stage0, int flip) {
     using D = Dims<KIND>;
     using LR = LinRec<KIND>;
     constexpr int NX = D::NX, NU = D::NU, F = LR::LEN;
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    const int stage = blockIdx.y;
+    const int stage = stage0 + blockIdx.y;   // stage0 > 0: one chunk of the horizon (see run_forward_overlapped)
     if (b >= prm.B || w.status[b] != TRAJOPT_RUNNING) return;
     const int Nb = w.Nb[b];
     if (stage > Nb) return;                  // beyond this problem's horizon
     const int Bp = prm.Bp;
-    const double* X = w.X[w.sel[b]];
-    const double* U = w.U[w.sel[b]];
+    const int cur = w.sel[b] ^ flip;         // flip = 1: the trajectory a rollout is writing, before it is accepted
+    const double* X = w.X[cur];
+    const double* U = w.U[cur];
     double rr[REFB ? RefRow<KIND>::N : 1];
     const double* refrow;
     if constexpr (REFB) {

@@ -205,7 +205,7 @@ template <int KIND> struct FwdSmem {
 };
 
 template <int KIND>
-__global__ void __launch_bounds__(kBlock) k_forward_ms_full(const Params prm, Work w) {
+__global__ void __launch_bounds__(kBlock) k_forward_ms_full(const Params prm, Work w, int i0, int i1) {
     using D = Dims<KIND>;
     using LR = LinRec<KIND>;
     using FS = FwdSmem<KIND>;
@@ -252,16 +252,21 @@ __global__ void __launch_bounds__(kBlock) k_forward_ms_full(const Params prm, Wo
                          : "memory");
         }
     };
-    issue(0, 0);
-    if (N > 1) issue(1, 1);
+    // stages [i0, i1) of the horizon: the whole of it, or one chunk (run_forward_overlapped), resuming from x_new(i0)
+    issue(i0, i0 & 1);
+    if (i0 + 1 < i1) issue(i0 + 1, (i0 + 1) & 1);
 
     State<KIND> xnew, x, xnext;
-    load_state<KIND>(X, 0, Bp, b, x);
-    xnew = x;
-    if (act) store_state<KIND>(Xn, 0, Bp, b, xnew);
+    load_state<KIND>(X, i0, Bp, b, x);
+    if (i0 == 0) {
+        xnew = x;
+        if (act) store_state<KIND>(Xn, 0, Bp, b, xnew);
+    } else {
+        load_state<KIND>(Xn, i0, Bp, b, xnew);
+    }
     uint32_t ph0 = 0, ph1 = 0;
-    const int Nb = w.Nb[b];              // this problem's horizon; the staging below runs over the group's N stages
-    for (int i = 0; i < N; ++i) {
+    const int Nb = w.Nb[b];              // this problem's horizon; the staging below runs over the group's stages
+    for (int i = i0; i < i1; ++i) {
         const int buf = i & 1;
         const bool live = act && (i < Nb);
         // independent of the recursion: issue these loads first
@@ -291,7 +296,7 @@ __global__ void __launch_bounds__(kBlock) k_forward_ms_full(const Params prm, Wo
             unew[a] = u + s;
         }
         __syncwarp();                       // every lane is done with this buffer
-        if (i + 2 < N) issue(i + 2, buf);
+        if (i + 2 < i1) issue(i + 2, buf);
         if (live) {
 #pragma unroll
             for (int a = 0; a < NU; ++a) Un[soa(i, a, NU, Bp, b)] = unew[a];
