@@ -44,6 +44,7 @@ template <int KIND> struct B3Smem {
     static constexpr int DOUBLES = REC_OFF + LR::STAGE_LEN;
     static constexpr int REC_BYTES = LR::STAGE_LEN * 32 * 8;
     static constexpr size_t BYTES = (size_t)DOUBLES * 32 * 8 + 16 + 32 * sizeof(int);   // + mbarrier + per-lane flags
+    static constexpr size_t GROUP_BYTES = (BYTES + 127) / 128 * 128;                     // stride between the groups of one CTA
 };
 
 __host__ __device__ constexpr int b3_ycol(int c) { return c < 6 ? c : c - 3; }   // smem slot of Y column c (c in 0..5, 9..11)
@@ -364,17 +365,22 @@ TO_DEV void b3_store_block(double* __restrict__ Vs, const double (&acc)[3][3], b
 
 // VH: per-problem horizons (trajopt_set_horizons).  Without it every `vlive` below folds to true and the stores are
 // unpredicated, which is worth 9% of the sweep at the headline size.
-template <int KIND, bool MS, bool VH>
-__global__ void __launch_bounds__(kB3Threads, 4) k_backward3(const Params prm, Work w, int it) {
+// G: groups of 32 problems per CTA (2 warps each).  With G > 1 the groups share the CTA-wide barriers and so march through
+// the stage body in step: a line of its ~110 KB of straight-line code is fetched once for all of them.
+template <int KIND, bool MS, bool VH, int G>
+__global__ void __launch_bounds__(kB3Threads * G, 4 / G) k_backward3(const Params prm, Work w, int it) {
     static_assert(!on_so3(KIND), "the 3-warp sweep is for the 12-dimensional families");
     using D = Dims<KIND>;
     using LR = LinRec<KIND>;
     using SM = B3Smem<KIND>;
     constexpr int NX = D::NX, NP = D::NP, NU = D::NU, NV = NX - NP, F = LR::LEN, NYC = SM::NYC;
-    extern __shared__ __align__(128) double sm[];
+    extern __shared__ __align__(128) double sm_cta[];
     const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    const int b = blockIdx.x * 32 + lane;
+    const int warp = (threadIdx.x >> 5) & 1;
+    const int tid = threadIdx.x & (kB3Threads - 1);   // thread within its group
+    const int grp = threadIdx.x / kB3Threads;
+    double* sm = sm_cta + (size_t)grp * (SM::GROUP_BYTES / 8);
+    const int b = (blockIdx.x * G + grp) * 32 + lane;
     const int N = prm.N, Np1 = N + 1;     // record layout / loop extent; the problem's own horizon is Nb <= N
     const int Nb = VH ? w.Nb[b < prm.Bp ? b : 0] : N;
     const size_t Bp = (size_t)prm.Bp;
@@ -388,7 +394,12 @@ __global__ void __launch_bounds__(kB3Threads, 4) k_backward3(const Params prm, W
     int* flags = reinterpret_cast<int*>(sm + SM::DOUBLES * 32 + 2);
 
     bool act = (b < prm.B) && (w.status[b] == TRAJOPT_RUNNING);
-    if (__ballot_sync(0xffffffffu, act) == 0u) return;   // same lanes in every warp: the whole CTA leaves together
+    bool alive = __ballot_sync(0xffffffffu, act) != 0u;   // same lanes in both warps of a group: they agree
+    if constexpr (G == 1) {
+        if (!alive) return;                                // the whole CTA leaves together
+    } else {
+        if (!__syncthreads_or(alive)) return;              // a finished group stays for the barriers of the others
+    }
 
     const double* __restrict__ lin = w.lin;
     // record of stage s of this lane (global); fields are kRecStride apart
@@ -397,7 +408,8 @@ __global__ void __launch_bounds__(kB3Threads, 4) k_backward3(const Params prm, W
     constexpr size_t kStageDoubles = (size_t)F * 32;
 
     // ---- cost / defect of the current trajectory (warp 0), terminal condition (warps 1, 2) --------
-    if (warp == 0) {
+    if (!alive) {
+    } else if (warp == 0) {
         int ok = act ? 1 : 0;
         if (act) {
             double Jcur, dn = 0.0;
@@ -439,26 +451,45 @@ __global__ void __launch_bounds__(kB3Threads, 4) k_backward3(const Params prm, W
 #pragma unroll
         for (int j = 0; j < NX; ++j) Vxs[j * 32] = g[(size_t)(LR::LX_OFF + j) * kRecStride];
     }
-    if (threadIdx.x == 0) b3_mbar_init(bar, 1);
+    if (alive && tid == 0) b3_mbar_init(bar, 1);
     __syncthreads();
-    act = flags[lane] != 0;
-    if (__ballot_sync(0xffffffffu, act) == 0u) return;
-    if (threadIdx.x == 0) b3_tma_load(rec_addr, group_base + (size_t)(N - 1) * kStageDoubles, SM::REC_BYTES, bar);
+    if (alive) {
+        act = flags[lane] != 0;
+        alive = __ballot_sync(0xffffffffu, act) != 0u;
+    }
+    if constexpr (G == 1) {
+        if (!alive) return;
+    } else {
+        if (!__syncthreads_or(alive)) return;
+    }
+    if (alive && tid == 0) b3_tma_load(rec_addr, group_base + (size_t)(N - 1) * kStageDoubles, SM::REC_BYTES, bar);
 
     double pad[NX];   // SS, warp 1: adjoint variable p (:2339)
     if constexpr (!MS) {
-        if (warp == 1) {
+        if (warp == 1 && alive) {
 #pragma unroll
             for (int j = 0; j < NX; ++j) pad[j] = Vxs[j * 32];
         }
     }
 
-    double mu = w.mu[b], delta = w.delta[b];
+    double mu = 0.0, delta = 0.0;
+    if (alive) {
+        mu = w.mu[b];
+        delta = w.delta[b];
+    }
     double gsum = 0.0;
     int flag_bits = 0;
     uint32_t parity = 0;
 
     for (int i = N - 1; i >= 0; --i) {
+        if constexpr (G > 1) {
+            if (!alive) {   // the three barriers of a stage
+                __syncthreads();
+                __syncthreads();
+                __syncthreads();
+                continue;
+            }
+        }
         const double* __restrict__ grec = grec_of(i);
         bool live = act && (!VH || i < Nb);   // stages beyond a problem's horizon only keep the barriers company
 #define vlive (VH ? live : true)
@@ -467,7 +498,7 @@ __global__ void __launch_bounds__(kB3Threads, 4) k_backward3(const Params prm, W
             const char* nxt = (const char*)(group_base + (size_t)(i - 2) * kStageDoubles);
 #pragma unroll
             for (int t = 0; t < (F * 2 + kB3Threads - 1) / kB3Threads; ++t) {
-                const int line = t * kB3Threads + (int)threadIdx.x;
+                const int line = t * kB3Threads + tid;
                 if (line < F * 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + (size_t)line * 128));
             }
         }
@@ -751,12 +782,12 @@ __global__ void __launch_bounds__(kB3Threads, 4) k_backward3(const Params prm, W
             }
         }
         __syncthreads();   // V(i), V_x(i) complete; nobody reads this stage's record any more
-        if (threadIdx.x == 0 && i > 0)
+        if (tid == 0 && i > 0)
             b3_tma_load(rec_addr, group_base + (size_t)(i - 1) * kStageDoubles, SM::REC_BYTES, bar);
     }
 
     const bool owner = MS ? (warp == 0) : (warp == 1);   // who accumulated the gradient norm
-    const bool was_running = flags[lane] != 0;
+    const bool was_running = alive && flags[lane] != 0;
     if (warp == 0 && was_running) {
         w.mu[b] = mu;
         w.delta[b] = delta;
