@@ -112,6 +112,20 @@ int trajopt_set_reference(trajopt_handle* h, const double* h_q_ref, const double
  * (traopt_cost.py:614-616) of problem b then use reference b. */
 int trajopt_set_reference_batch(trajopt_handle* h, const double* d_q_ref, const double* d_xi_ref, void* stream);
 
+/* Continuous batching: n_problems (>= 0, any number) problems through the handle's B slots.  A slot whose problem has
+ * finished is given the next x0 of the queue before the following DDP iteration, so every launch works on (nearly) B
+ * running problems instead of waiting for the slowest of a batch.  Problem p's result is the one trajopt_solve gives for
+ * the same x0 (a problem's arithmetic does not depend on its slot); it is written to row p of the output arrays
+ * (DEVICE pointers, sized for n_problems; any may be NULL): d_xs [n][N+1][NS], d_us [n][N][NU], d_J, d_iters,
+ * d_status, d_grad, d_defect [n].  d_x0 [n][NS] device; d_us_init NULL (zeros) or ONE [N][NU] initial control sequence
+ * shared by all problems.  Single and multiple shooting (with or without line search); not the augmented-Lagrangian
+ * method, per-problem references or per-problem horizons (those belong to a batch: trajopt_solve).
+ * The reference's counterpart is its joblib pool handing the next job to whichever worker is free
+ * (visualization/perturb_all_compute.py:240-250). */
+int trajopt_solve_stream(trajopt_handle* h, const double* d_x0, int64_t n_problems, const double* d_us_init, double* d_xs,
+                         double* d_us, double* d_J, int32_t* d_iters, int32_t* d_status, double* d_grad, double* d_defect,
+                         void* stream);
+
 /* One horizon per problem: DEVICE pointer d_N [B], clamped to [1, N]; NULL restores N for every problem.  Problem b
  * then is the N_b-stage problem on the first N_b + 1 rows of its reference (terminal cost at stage N_b); rows of the
  * exported trajectories beyond N_b hold the initial guess.  Set before trajopt_begin. */

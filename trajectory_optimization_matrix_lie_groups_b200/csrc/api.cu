@@ -91,6 +91,7 @@ int trajopt_create(int kind, int method, int N, int B, int device, trajopt_handl
     A_(w.counters, 4);
     A_(w.orig, Bp);
     A_(w.Nb, Bp);
+    A_(w.slot_id, Bp); A_(w.fresh, Bp); A_(w.free_list, Bp); A_(w.done_list, Bp); A_(w.scnt, 4);
     A_(h->d_dweight, Bp);
     if (method == TRAJOPT_AL_MS) {
         A_(w.lam, Np1 * 2 * h->NU * Bp); A_(w.imu, Np1 * 2 * h->NU * Bp);
@@ -380,6 +381,25 @@ int trajopt_solve(trajopt_handle* h, const double* d_x0, const double* d_us_init
     rc = trajopt_iterate(h, units, &active, stream);
     if (rc) return rc;
     return trajopt_export(h, d_xs, d_us, d_J, d_iters, d_status, d_grad, d_defect, stream);
+}
+
+int trajopt_solve_stream(trajopt_handle* h, const double* d_x0, int64_t n_problems, const double* d_us_init, double* d_xs,
+                         double* d_us, double* d_J, int32_t* d_iters, int32_t* d_status, double* d_grad, double* d_defect,
+                         void* stream) {
+    if (!h || !d_x0) return fail(TRAJOPT_E_INVALID, "trajopt_solve_stream: NULL argument");
+    if (!h->have_params || !h->have_ref) return fail(TRAJOPT_E_STATE, "trajopt_solve_stream: set parameters and reference first");
+    if (n_problems < 0 || n_problems > 0x7fffffff) return fail(TRAJOPT_E_INVALID, "trajopt_solve_stream: n_problems out of range");
+    if (h->method == TRAJOPT_AL_MS) return fail(TRAJOPT_E_INVALID, "trajopt_solve_stream: the augmented-Lagrangian outer loop is per batch; use trajopt_solve");
+    if (h->w.ref_batch || h->var_horizons)
+        return fail(TRAJOPT_E_INVALID, "trajopt_solve_stream: per-problem references / horizons belong to slots; use trajopt_solve");
+    DeviceGuard guard(h->device);
+    int rc = ensure_hist(h);
+    if (rc) return rc;
+    h->w.us_init = d_us_init;
+    h->w.us_mode = d_us_init ? 1 : 0;
+    h->begun = false;
+    return DISPATCH_KIND(h, solve_stream_impl, h, d_x0, (int)n_problems, d_xs, d_us, d_J, (int*)d_iters, (int*)d_status, d_grad,
+                         d_defect, (cudaStream_t)stream);
 }
 
 int trajopt_solve_host(trajopt_handle* h, const double* h_x0, const double* h_us_init, int us_mode, double* h_xs,

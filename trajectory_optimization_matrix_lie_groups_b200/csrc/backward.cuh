@@ -88,7 +88,7 @@ template <int KIND> constexpr int bwd_smem_doubles() {
 // LPW = problems (active lanes) per warp: 32, or 16 to double the number of independent recursions in flight
 // when the batch alone cannot fill the schedulers (each CTA is ONE warp of LPW threads)
 template <int KIND, bool MS, int LPW>
-__global__ void __launch_bounds__(LPW) k_backward(const Params prm, Work w, int it) {
+__global__ void __launch_bounds__(LPW) k_backward(const Params prm, Work w, int it_arg) {
     using D = Dims<KIND>;
     using LR = LinRec<KIND>;
     constexpr int NX = D::NX, NP = D::NP, NU = D::NU, NV = NX - NP, F = LR::LEN;
@@ -99,6 +99,7 @@ __global__ void __launch_bounds__(LPW) k_backward(const Params prm, Work w, int 
     const int lane = threadIdx.x;
     const int b = blockIdx.x * LPW + lane;
     if (b >= prm.B || w.status[b] != TRAJOPT_RUNNING) return;
+    const int it = it_arg >= 0 ? it_arg : w.iters[b];   // < 0: every slot counts its own iterations (trajopt_solve_stream)
     const int N = prm.N;                 // record layout stride; the problem's own horizon is Nb
     const int Nb = w.Nb[b];
     const size_t Bp = (size_t)prm.Bp;

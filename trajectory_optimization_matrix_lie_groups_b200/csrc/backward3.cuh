@@ -368,7 +368,7 @@ TO_DEV void b3_store_block(double* __restrict__ Vs, const double (&acc)[3][3], b
 // G: groups of 32 problems per CTA (2 warps each).  With G > 1 the groups share the CTA-wide barriers and so march through
 // the stage body in step: a line of its ~110 KB of straight-line code is fetched once for all of them.
 template <int KIND, bool MS, bool VH, int G>
-__global__ void __launch_bounds__(kB3Threads * G, 4 / G) k_backward3(const Params prm, Work w, int it) {
+__global__ void __launch_bounds__(kB3Threads * G, 4 / G) k_backward3(const Params prm, Work w, int it_arg) {
     static_assert(!on_so3(KIND), "the 3-warp sweep is for the 12-dimensional families");
     using D = Dims<KIND>;
     using LR = LinRec<KIND>;
@@ -394,6 +394,7 @@ __global__ void __launch_bounds__(kB3Threads * G, 4 / G) k_backward3(const Param
     int* flags = reinterpret_cast<int*>(sm + SM::DOUBLES * 32 + 2);
 
     bool act = (b < prm.B) && (w.status[b] == TRAJOPT_RUNNING);
+    const int it = it_arg >= 0 ? it_arg : (act ? w.iters[b] : 0);   // < 0: per-slot iteration counts (trajopt_solve_stream)
     bool alive = __ballot_sync(0xffffffffu, act) != 0u;   // same lanes in both warps of a group: they agree
     if constexpr (G == 1) {
         if (!alive) return;                                // the whole CTA leaves together

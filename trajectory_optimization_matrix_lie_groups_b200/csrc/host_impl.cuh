@@ -43,6 +43,7 @@ struct trajopt_handle {
     cudaEvent_t ev_chunk[kMaxChunks] = {};
     cudaEvent_t ev_join = nullptr;
     bool lin_ready = false;
+    bool streaming = false;      // inside trajopt_solve_stream
     int it = 0;              // next inner iteration
     bool inner_done = true;  // the inner loop of the current fit() / AL outer iteration has ended
     int al_outer = 0;        // AL outer iterations completed
@@ -145,8 +146,8 @@ template <int KIND, bool MS>
 int run_linearize(trajopt_handle* h, cudaStream_t s) {
     PhaseTimer t(h, s, PH_LIN);
     dim3 grid(blocks_for(h->Bp, 128), h->N + 1);
-    if (h->w.ref_batch) LAUNCH((k_linearize<KIND, MS, true>), grid, 128, 0, s, h->prm, h->w, 0, 0);
-    else LAUNCH((k_linearize<KIND, MS, false>), grid, 128, 0, s, h->prm, h->w, 0, 0);
+    if (h->w.ref_batch) LAUNCH((k_linearize<KIND, MS, true>), grid, 128, 0, s, h->prm, h->w, 0, 0, (const int*)nullptr);
+    else LAUNCH((k_linearize<KIND, MS, false>), grid, 128, 0, s, h->prm, h->w, 0, 0, (const int*)nullptr);
     return 0;
 }
 
@@ -186,8 +187,8 @@ int run_forward_overlapped(trajopt_handle* h, cudaStream_t s, int chunks) {
         CUDA_OK(cudaStreamWaitEvent(s, h->ev_chunk[c], 0));
         const int s1 = (c == chunks - 1) ? N + 1 : i1;      // the last chunk takes the terminal stage along
         dim3 grid(bx, s1 - i0);
-        if (h->w.ref_batch) LAUNCH((k_linearize<KIND, true, true>), grid, lin_block, 0, s, h->prm, h->w, i0, 1);
-        else LAUNCH((k_linearize<KIND, true, false>), grid, lin_block, 0, s, h->prm, h->w, i0, 1);
+        if (h->w.ref_batch) LAUNCH((k_linearize<KIND, true, true>), grid, lin_block, 0, s, h->prm, h->w, i0, 1, (const int*)nullptr);
+        else LAUNCH((k_linearize<KIND, true, false>), grid, lin_block, 0, s, h->prm, h->w, i0, 1, (const int*)nullptr);
     }
     h->lin_ready = true;
     return 0;
@@ -258,7 +259,8 @@ inline int count_running(trajopt_handle* h, cudaStream_t s, int* out) {
 // one pass of the `for iteration in range(n_iterations)` body for every running problem
 template <int KIND>
 int inner_iteration(trajopt_handle* h, cudaStream_t s) {
-    const int it = h->it;
+    const int it = h->streaming ? -1 : h->it;    // streaming: every slot counts its own iterations (stream.cuh)
+    const bool roll = h->streaming || h->it < h->prm.max_iters;
     const int na = h->prm.n_alphas;
     const int bgrid = blocks_for(h->Bp, 128);
     int rc;
@@ -279,7 +281,7 @@ int inner_iteration(trajopt_handle* h, cudaStream_t s) {
         if (!h->lin_ready && (rc = run_linearize<KIND, true>(h, s))) return rc;
         h->lin_ready = false;
         if ((rc = run_backward<KIND, true>(h, s, it))) return rc;
-        if (it < h->prm.max_iters) {
+        if (roll) {
             if (h->prm.line_search) {
                 {
                     PhaseTimer t(h, s, PH_FWD);
@@ -308,7 +310,7 @@ int inner_iteration(trajopt_handle* h, cudaStream_t s) {
             }
         }
     }
-    h->it = it + 1;
+    h->it = h->it + 1;
     return 0;
 }
 
@@ -408,10 +410,10 @@ int start_inner(trajopt_handle* h, cudaStream_t s, bool al_restart) {
     if (al_restart) LAUNCH(k_reset_al_inner, bgrid, 128, 0, s, h->prm, h->w);
     else LAUNCH(k_reset, bgrid, 128, 0, s, h->prm, h->w);
     if (h->method == TRAJOPT_SS) {
-        LAUNCH((k_init_ss<KIND>), h->Bp / kBlock, kBlock, 0, s, h->prm, h->w);
+        LAUNCH((k_init_ss<KIND>), h->Bp / kBlock, kBlock, 0, s, h->prm, h->w, (const int*)nullptr);
     } else {
         dim3 grid(bgrid, h->N + 1);
-        LAUNCH((k_init_ms<KIND>), grid, 128, 0, s, h->prm, h->w, al_restart);
+        LAUNCH((k_init_ms<KIND>), grid, 128, 0, s, h->prm, h->w, al_restart, (const int*)nullptr);
         if (h->prm.line_search) {
             std::vector<double> dw((size_t)h->Bp, h->prm.defect_mu0);
             CUDA_OK(cudaMemcpyAsync(h->d_dweight, dw.data(), dw.size() * sizeof(double), cudaMemcpyHostToDevice, s));
@@ -539,11 +541,15 @@ inline int ensure_hist(trajopt_handle* h) {
 
 }  // namespace trajopt_host
 
-// the four entry points api.cu dispatches on the family
+#include "stream.cuh"
+
+// the entry points api.cu dispatches on the family
 #define TRAJOPT_KIND_INSTANTIATE(K)                                                                                             \
     template int trajopt_host::set_reference_batch_impl<K>(trajopt_handle*, const double*, const double*, cudaStream_t);        \
     template int trajopt_host::begin_impl<K>(trajopt_handle*, const double*, const double*, int, cudaStream_t);                  \
     template int trajopt_host::iterate_impl<K>(trajopt_handle*, int, int*, cudaStream_t);                                        \
+    template int trajopt_host::solve_stream_impl<K>(trajopt_handle*, const double*, int, double*, double*, double*, int*, int*, \
+                                                    double*, double*, cudaStream_t);                                             \
     template int trajopt_host::debug_linearize_impl<K>(trajopt_handle*, double*, double*, double*, double*, double*, double*,   \
                                                        double*, cudaStream_t);                                                   \
     template int trajopt_host::debug_stage_impl<K>(trajopt_handle*, int, int, int, const double*, const double*, double*,       \
@@ -552,6 +558,8 @@ inline int ensure_hist(trajopt_handle* h) {
     extern template int trajopt_host::set_reference_batch_impl<K>(trajopt_handle*, const double*, const double*, cudaStream_t); \
     extern template int trajopt_host::begin_impl<K>(trajopt_handle*, const double*, const double*, int, cudaStream_t);           \
     extern template int trajopt_host::iterate_impl<K>(trajopt_handle*, int, int*, cudaStream_t);                                 \
+    extern template int trajopt_host::solve_stream_impl<K>(trajopt_handle*, const double*, int, double*, double*, double*,      \
+                                                           int*, int*, double*, double*, cudaStream_t);                          \
     extern template int trajopt_host::debug_linearize_impl<K>(trajopt_handle*, double*, double*, double*, double*, double*,     \
                                                               double*, double*, cudaStream_t);                                   \
     extern template int trajopt_host::debug_stage_impl<K>(trajopt_handle*, int, int, int, const double*, const double*,         \

@@ -53,6 +53,12 @@ struct Work {
     double* al_viol;     // [Bp]
     int* al_done;        // [Bp]
     int* counters;       // [0] running problems, [1] pending line searches, [2] AL problems not converged
+    // trajopt_solve_stream (stream.cuh): problem id held by a slot (-1: empty), refill flags, slot lists, counters
+    int* slot_id;        // [Bp]
+    int* fresh;          // [Bp]
+    int* free_list;      // [Bp]
+    int* done_list;      // [Bp]
+    int* scnt;           // [4] free slots, finished problems to export, running slots
     int* Nb;             // [Bp] horizon of each problem, 1 <= Nb <= N (trajopt_set_horizons; default N for all)
     int* orig;           // [Bp] slot -> problem index of the caller (identity until a compaction moves problems)
 };
@@ -318,12 +324,13 @@ static __global__ void k_reset_al_inner(const Params prm, Work w) {
 
 // Multiple shooting initial guess: shooting nodes = reference (:3123-3136); controls = us_init
 template <int KIND>
-__global__ void k_init_ms(const Params prm, Work w, bool only_running) {
+__global__ void k_init_ms(const Params prm, Work w, bool only_running, const int* __restrict__ mask) {
     constexpr int NS = Dims<KIND>::NS, NU = Dims<KIND>::NU;
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     const int stage = blockIdx.y;
     if (b >= prm.Bp) return;
     if (only_running && w.status[b] != TRAJOPT_RUNNING) return;
+    if (mask && !mask[b]) return;            // trajopt_solve_stream: only the slots that were just refilled
     State<KIND> s;
     if (stage == 0) {
 #pragma unroll
@@ -352,10 +359,11 @@ __global__ void k_init_ms(const Params prm, Work w, bool only_running) {
 
 // Single shooting initial rollout (:2015-2028)
 template <int KIND>
-__global__ void __launch_bounds__(kBlock) k_init_ss(const Params prm, Work w) {
+__global__ void __launch_bounds__(kBlock) k_init_ss(const Params prm, Work w, const int* __restrict__ mask) {
     constexpr int NU = Dims<KIND>::NU;
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= prm.Bp) return;
+    if (mask && !mask[b]) return;
     State<KIND> x, xn;
 #pragma unroll
     for (int j = 0; j < 4; ++j) x.q[j] = w.x0[(size_t)j * prm.Bp + b];
@@ -389,13 +397,14 @@ __global__ void __launch_bounds__(kBlock) k_init_ss(const Params prm, Work w) {
 // 3 blocks per SM (168 registers, 52 bytes of spills): 3.60 -> 3.29 ms at 16384 x 955 once the state part of the record is
 // stored before the dynamics part is formed; 4 blocks (128 registers, 450 bytes of spills) is slower again (3.67 ms).
 template <int KIND, bool MS, bool REFB>
-__global__ void __launch_bounds__(128, 3) k_linearize(const Params prm, Work w, int stage0, int flip) {
+__global__ void __launch_bounds__(128, 3) k_linearize(const Params prm, Work w, int stage0, int flip, const int* __restrict__ mask) {
     using D = Dims<KIND>;
     using LR = LinRec<KIND>;
     constexpr int NX = D::NX, NU = D::NU, F = LR::LEN;
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     const int stage = stage0 + blockIdx.y;   // stage0 > 0: one chunk of the horizon (see run_forward_overlapped)
     if (b >= prm.B || w.status[b] != TRAJOPT_RUNNING) return;
+    if (mask && !mask[b]) return;            // trajopt_solve_stream: only the slots that were just refilled
     const int Nb = w.Nb[b];
     if (stage > Nb) return;                  // beyond this problem's horizon
     const int Bp = prm.Bp;

@@ -317,9 +317,10 @@ __global__ void __launch_bounds__(kBlock) k_forward_ms_full(const Params prm, Wo
 }
 
 // MS without line search: alpha = 1 is always accepted (:2592-2600)
-static __global__ void k_accept_all(const Params prm, Work w, int it) {
+static __global__ void k_accept_all(const Params prm, Work w, int it_arg) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= prm.B || w.status[b] != TRAJOPT_RUNNING) return;
+    const int it = it_arg >= 0 ? it_arg : w.iters[b];
     w.sel[b] = 1 - w.sel[b];
     w.alphahist[(size_t)it * prm.Bp + b] = 0;
     w.iters[b] = it + 1;
@@ -336,9 +337,10 @@ static __global__ void k_count_running(const Params prm, Work w) {
 // SS line search (:1972-1990): examine candidates [a_lo, a_lo+a_cnt) in index order, accept the
 // first J_new < J_opt.  first pass (a_lo == 0): the accepted trajectory is already in the other
 // buffer; later passes only pick the index and a final k_forward<WRITE> materialises it.
-static __global__ void k_ls_select_ss(const Params prm, Work w, int it, int a_lo, int a_cnt, int last) {
+static __global__ void k_ls_select_ss(const Params prm, Work w, int it_arg, int a_lo, int a_cnt, int last) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     const bool in = (b < prm.B) && (w.status[b] == TRAJOPT_RUNNING);
+    const int it = it_arg >= 0 ? it_arg : (in ? w.iters[b] : 0);
     bool pending = false;
     if (in && (a_lo == 0 || w.ls_state[b] == -1)) {
         const double Jopt = w.J[b];
@@ -365,9 +367,10 @@ static __global__ void k_ls_select_ss(const Params prm, Work w, int it, int a_lo
 }
 
 // commit an accepted SS candidate whose trajectory is in the other buffer
-static __global__ void k_ls_commit_ss(const Params prm, Work w, int it) {
+static __global__ void k_ls_commit_ss(const Params prm, Work w, int it_arg) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= prm.B || w.status[b] != TRAJOPT_RUNNING) return;
+    const int it = it_arg >= 0 ? it_arg : w.iters[b];
     const int a = w.ls_state[b];
     if (a < 0) return;
     const double Jn = w.Jcand[(size_t)a * prm.Bp + b];
@@ -502,9 +505,10 @@ __global__ void __launch_bounds__(kBlock) k_ms_expected(const Params prm, Work w
 }
 
 // accept the first alpha with merit_new - merit < gamma (dJ_exp(alpha) - alpha w ||d||) (:2576)
-static __global__ void k_ls_select_ms(const Params prm, Work w, int it, int a_lo, int a_cnt, int last) {
+static __global__ void k_ls_select_ms(const Params prm, Work w, int it_arg, int a_lo, int a_cnt, int last) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     const bool in = (b < prm.B) && (w.status[b] == TRAJOPT_RUNNING);
+    const int it = it_arg >= 0 ? it_arg : (in ? w.iters[b] : 0);
     bool pending = false;
     const int Bp = prm.Bp;
     if (in && (a_lo == 0 || w.ls_state[b] == -1)) {
@@ -539,9 +543,10 @@ static __global__ void k_ls_select_ms(const Params prm, Work w, int it, int a_lo
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(&w.counters[1], __popc(m));
 }
 
-static __global__ void k_ls_commit_ms(const Params prm, Work w, int it) {
+static __global__ void k_ls_commit_ms(const Params prm, Work w, int it_arg) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= prm.B || w.status[b] != TRAJOPT_RUNNING) return;
+    const int it = it_arg >= 0 ? it_arg : w.iters[b];
     const int a = w.ls_state[b];
     if (a < 0) return;
     w.sel[b] = 1 - w.sel[b];

@@ -211,6 +211,33 @@ class BatchSolver:
         self.iterate(units)
         return self.export(trajectories)
 
+    def solve_stream(self, x0, us_init=None, trajectories=True, out=None):
+        """Continuous batching: any number M of problems through this solver's B slots (`trajopt_solve_stream`).
+
+        x0: (M, NS) device tensor / array.  us_init: None or ONE (N, NU) sequence shared by all problems.
+        Returns the same dict as `solve`, with M rows; problem p's row is what `solve` returns for x0[p].
+        `out`: optional dict of preallocated device tensors to fill (bench: no allocation in the timed region).
+        """
+        x0 = torch.as_tensor(x0, dtype=torch.float64)
+        if x0.device != self.device:
+            x0 = x0.to(self.device)
+        x0 = x0.contiguous()
+        if x0.ndim != 2 or x0.shape[1] != self.NS:
+            raise ValueError(f"x0 must be (M, {self.NS})")
+        M, N = x0.shape[0], self.N
+        us_t = None if us_init is None else self._dev(us_init, (N, self.NU))
+        if out is None:
+            out = {"J": self._new(M), "iters": self._new(M, dtype=torch.int32), "status": self._new(M, dtype=torch.int32),
+                   "grad": self._new(M), "defect": self._new(M),
+                   "xs": self._new(M, N + 1, self.NS) if trajectories else None,
+                   "us": self._new(M, N, self.NU) if trajectories else None}
+        if M == 0:
+            return out
+        check(lib.trajopt_solve_stream(self._h, _ptr(x0), M, _ptr(us_t), _ptr(out["xs"]), _ptr(out["us"]), _ptr(out["J"]),
+                                       _ptr(out["iters"]), _ptr(out["status"]), _ptr(out["grad"]), _ptr(out["defect"]),
+                                       _stream(self.device)))
+        return out
+
     def solve_host(self, x0, us_init=None, trajectories=True, out=None):
         """Same through HOST buffers (NumPy, ideally pinned): H2D, solve, D2H inside one call."""
         B, N = self.B, self.N
