@@ -148,9 +148,14 @@ def workload_config(args, wl):
         "perturbation": "one of 12 x0 parameters per problem, +-10% of the reference sweep half-width, seed 24234156",
         "l2": "working set (trajectories, linearisation, gains: tens of GB) far exceeds the 126 MB L2; no flush needed",
         "parallelism": f"dp{args.gpus} (independent problems, contiguous shards)",
-        "inflight": max(1, args.inflight),
-        "inflight_note": "batches in flight per GPU (own stream + host thread each); the tail of one batch's solve, where most "
-                         "problems have converged and most CTAs exit at once, overlaps the head of the next; steps complete in order",
+        "schedule": args.schedule,
+        "schedule_note": ("continuous batching (trajopt_solve_stream): the problems of the timed steps are one queue through "
+                          "batch_per_gpu solver slots; a slot whose problem has finished takes the next problem before the following "
+                          "DDP iteration; every problem's result is bit-identical to a plain batched solve (asserted here)")
+        if args.schedule == "stream" else
+        ("whole batches, `inflight` of them per GPU (own stream + host thread each); the tail of one batch's solve, where most "
+         "problems have converged and most CTAs exit at once, overlaps the head of the next; steps complete in order"),
+        "inflight": 1 if args.schedule == "stream" else max(1, args.inflight),
     }
 
 
@@ -224,7 +229,8 @@ def run_gpu_arm(args):
 
     B = args.batch
     wl = workloads.CONFIGS[args.config](B=B * world)
-    depth = max(1, args.inflight)
+    stream_mode = args.schedule == "stream"
+    depth = 1 if stream_mode else max(1, args.inflight)
     x0_rows = wl.x0_rows[rank * B:rank * B + B]
     pipe = PipelinedSolver(lambda: wl.make_solver(B=B, device=dev, offset=rank * B)[0], depth=depth, device=dev)
     solver = pipe.solvers[0]
@@ -243,7 +249,23 @@ def run_gpu_arm(args):
              "xs": torch.empty(B, wl.N + 1, solver.NS, dtype=torch.float64).pin_memory() if want_traj else None,
              "us": torch.empty(B, wl.N, solver.NU, dtype=torch.float64).pin_memory() if want_traj else None}
         return o, {k: (None if v is None else v.numpy()) for k, v in o.items()}
-    outs = [pinned_out() for _ in range(depth)]        # one set of pinned result buffers per lane
+    outs = [pinned_out() for _ in range(depth)] if not stream_mode else []   # one set of pinned result buffers per lane
+    if stream_mode:
+        # continuous batching: the problems of n steps are ONE queue of n x B problems through the solver's B slots
+        n_max = max(args.steps, args.warmup, 1)
+        x0_all_dev = x0_dev.repeat(n_max, 1)
+        x0_all_pin = torch.as_tensor(np.tile(x0_rows, (n_max, 1))).pin_memory()
+        M = n_max * B
+        dev_out = {"J": torch.empty(M, dtype=torch.float64, device=dev), "grad": torch.empty(M, dtype=torch.float64, device=dev),
+                   "defect": torch.empty(M, dtype=torch.float64, device=dev), "iters": torch.empty(M, dtype=torch.int32, device=dev),
+                   "status": torch.empty(M, dtype=torch.int32, device=dev), "xs": None, "us": None}
+        ns = args.steps
+        host_out_t = {"J": torch.empty(ns * B, dtype=torch.float64).pin_memory(), "grad": torch.empty(ns * B, dtype=torch.float64).pin_memory(),
+                      "defect": torch.empty(ns * B, dtype=torch.float64).pin_memory(),
+                      "iters": torch.empty(ns * B, dtype=torch.int32).pin_memory(), "status": torch.empty(ns * B, dtype=torch.int32).pin_memory(),
+                      "xs": torch.empty(ns * B, wl.N + 1, solver.NS, dtype=torch.float64).pin_memory() if want_traj else None,
+                      "us": torch.empty(ns * B, wl.N, solver.NU, dtype=torch.float64).pin_memory() if want_traj else None}
+        host_out = {k: (None if v is None else v.numpy()) for k, v in host_out_t.items()}
     gathered = [torch.empty(B, 5, dtype=torch.float64, device=dev) for _ in range(world)] if world > 1 else None
 
     def gather(out):
@@ -253,6 +275,20 @@ def run_gpu_arm(args):
 
     def run_steps(n, host):
         """n steps, `depth` batches in flight; steps complete (and are gathered) in submission order."""
+        if stream_mode:
+            if host:
+                n = min(n, args.steps)
+                o = solver.solve_stream_host(x0_all_pin.numpy()[: n * B], trajectories=want_traj,
+                                             out={k: (None if v is None else v[: n * B]) for k, v in host_out.items()})
+                return {k: (None if v is None else v[(n - 1) * B: n * B]) for k, v in o.items()}
+            o = solver.solve_stream(x0_all_dev[: n * B], trajectories=False,
+                                    out={k: (None if v is None else v[: n * B]) for k, v in dev_out.items()})
+            torch.cuda.current_stream(dev).synchronize()
+            last = None
+            for k in range(n):
+                last = {key: (None if v is None else v[k * B:(k + 1) * B]) for key, v in o.items()}
+                gather(last)
+            return last
         futs = []
         for k in range(n):
             if host:
@@ -306,7 +342,10 @@ def run_gpu_arm(args):
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     h2d = x0_rows.nbytes
-    out_np = outs[(args.steps - 1) % depth][1]
+    if stream_mode:
+        out_np = {k: (None if v is None else v[(args.steps - 1) * B: args.steps * B]) for k, v in host_out.items()}
+    else:
+        out_np = outs[(args.steps - 1) % depth][1]
     d2h = sum(v.nbytes for v in out_np.values() if v is not None)
     assert np.array_equal(out_np["iters"], iters), "host-buffer path and device path disagree"
 
@@ -424,12 +463,18 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--inflight", type=int, default=0,
                     help="batches in flight per GPU (1 = strictly one after the other; 0 = auto: 2, or 8 for batches <= 2048)")
+    ap.add_argument("--schedule", default="pipelined", choices=["stream", "pipelined"],
+                    help="pipelined (default): whole batches, --inflight of them at a time; stream: continuous batching, the K "
+                         "steps' problems are one queue through batch_per_gpu slots (trajopt_solve_stream) — measured slower on "
+                         "the headline workload (32.6 k against 37.8 k solves/s, see DESIGN.md section 5)")
     ap.add_argument("--compact", default="", help="'min_batch,ratio' for trajopt_set_compaction (default: the library's 1024,4; '-1,4' = off)")
     args = ap.parse_args()
     if args.batch is None:
         args.batch = {1: 1, 2: 1024, 3: 16384, 4: 2048, 5: 131072}[args.config]
     if args.inflight <= 0:
         args.inflight = 2 if args.batch > 2048 else 8
+    if args.schedule == "stream" and args.config == 4:
+        raise SystemExit("--schedule stream: the augmented-Lagrangian method is solved per batch (use pipelined)")
     if args.impl == "reference":
         return run_reference_arm(args)
     return run_gpu_arm(args)

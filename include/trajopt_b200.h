@@ -126,6 +126,12 @@ int trajopt_solve_stream(trajopt_handle* h, const double* d_x0, int64_t n_proble
                          double* d_us, double* d_J, int32_t* d_iters, int32_t* d_status, double* d_grad, double* d_defect,
                          void* stream);
 
+/* The same through HOST buffers (pinned for full speed): x0 goes up once, and the rows of the problems that are
+ * complete (every id below the lowest one still running) leave for the host on a side stream while the solve goes on. */
+int trajopt_solve_stream_host(trajopt_handle* h, const double* h_x0, int64_t n_problems, const double* h_us_init, double* h_xs,
+                              double* h_us, double* h_J, int32_t* h_iters, int32_t* h_status, double* h_grad, double* h_defect,
+                              void* stream);
+
 /* One horizon per problem: DEVICE pointer d_N [B], clamped to [1, N]; NULL restores N for every problem.  Problem b
  * then is the N_b-stage problem on the first N_b + 1 rows of its reference (terminal cost at stage N_b); rows of the
  * exported trajectories beyond N_b hold the initial guess.  Set before trajopt_begin. */

@@ -41,6 +41,9 @@ def test_stream_matches_batched_solves(name, method, kw, M):
     assert it.min() < it.max()                      # the refill path is really exercised
     for k in ("iters", "status", "J", "grad", "defect", "us", "xs"):
         assert torch.equal(out[k], ref[k]), k
+    host = s.solve_stream_host(X0)                  # host buffers, rows copied out while the solve goes on
+    for k in ("iters", "status", "J", "grad", "defect", "us", "xs"):
+        assert np.array_equal(host[k], ref[k].cpu().numpy()), k
     # and again with the same handle: no state leaks from one stream to the next, or into plain solves
     out2 = s.solve_stream(X0[: M // 2], trajectories=False)
     assert torch.equal(out2["J"], ref["J"][: M // 2]) and out2["xs"] is None

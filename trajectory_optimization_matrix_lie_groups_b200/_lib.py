@@ -73,6 +73,7 @@ SYMBOLS = {
     "trajopt_set_reference_batch": (_I, [_P, _P, _P, _P]),
     "trajopt_set_horizons": (_I, [_P, _P, _P]),
     "trajopt_solve_stream": (_I, [_P, _P, C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "trajopt_solve_stream_host": (_I, [_P, _P, C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "trajopt_begin": (_I, [_P, _P, _P, _I, _P]),
     "trajopt_iterate": (_I, [_P, _I, C.POINTER(_I), _P]),
     "trajopt_export": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P]),

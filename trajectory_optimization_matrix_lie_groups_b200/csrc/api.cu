@@ -136,6 +136,9 @@ int trajopt_destroy(trajopt_handle* h) {
     for (cudaEvent_t e : h->ev_chunk) if (e) cudaEventDestroy(e);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->s2) cudaStreamDestroy(h->s2);
+    if (h->s_copy) cudaStreamDestroy(h->s_copy);
+    for (void* p : h->so_buf) if (p) cudaFree(p);
+    if (h->so_x0) cudaFree(h->so_x0);
     delete h;
     return 0;
 }
@@ -400,6 +403,64 @@ int trajopt_solve_stream(trajopt_handle* h, const double* d_x0, int64_t n_proble
     h->begun = false;
     return DISPATCH_KIND(h, solve_stream_impl, h, d_x0, (int)n_problems, d_xs, d_us, d_J, (int*)d_iters, (int*)d_status, d_grad,
                          d_defect, (cudaStream_t)stream);
+}
+
+int trajopt_solve_stream_host(trajopt_handle* h, const double* h_x0, int64_t n_problems, const double* h_us_init, double* h_xs,
+                              double* h_us, double* h_J, int32_t* h_iters, int32_t* h_status, double* h_grad, double* h_defect,
+                              void* stream) {
+    if (!h || !h_x0) return fail(TRAJOPT_E_INVALID, "trajopt_solve_stream_host: NULL argument");
+    if (n_problems < 0 || n_problems > 0x7fffffff) return fail(TRAJOPT_E_INVALID, "trajopt_solve_stream_host: n_problems out of range");
+    DeviceGuard guard(h->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t n = (size_t)n_problems, N = h->N;
+    void* host[7] = {h_xs, h_us, h_J, h_iters, h_status, h_grad, h_defect};
+    const size_t row[7] = {(N + 1) * h->NS * 8, N * h->NU * 8, 8, 4, 4, 8, 8};   // bytes per problem
+    for (int k = 0; k < 7; ++k) {
+        if (!host[k] || row[k] * n <= h->so_bytes[k]) continue;
+        if (h->so_buf[k]) cudaFree(h->so_buf[k]);
+        h->so_buf[k] = nullptr;
+        h->so_bytes[k] = 0;
+        CUDA_OK(cudaMalloc(&h->so_buf[k], row[k] * n));
+        h->so_bytes[k] = row[k] * n;
+    }
+    const size_t x0_bytes = n * h->NS * 8, us0_bytes = h_us_init ? N * h->NU * 8 : 0;
+    if (x0_bytes > h->so_x0_bytes) {
+        if (h->so_x0) cudaFree(h->so_x0);
+        h->so_x0 = nullptr;
+        h->so_x0_bytes = 0;
+        CUDA_OK(cudaMalloc((void**)&h->so_x0, x0_bytes));
+        h->so_x0_bytes = x0_bytes;
+    }
+    if (us0_bytes > h->s_us0_bytes) {
+        if (h->s_us0) cudaFree(h->s_us0);
+        h->s_us0 = nullptr;
+        CUDA_OK(cudaMalloc((void**)&h->s_us0, us0_bytes));
+        h->s_us0_bytes = us0_bytes;
+    }
+    if (!h->s_copy) CUDA_OK(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
+    if (n) CUDA_OK(cudaMemcpyAsync(h->so_x0, h_x0, x0_bytes, cudaMemcpyHostToDevice, s));
+    if (us0_bytes) CUDA_OK(cudaMemcpyAsync(h->s_us0, h_us_init, us0_bytes, cudaMemcpyHostToDevice, s));
+    // rows of problems [copied, upto) leave for the host on the copy stream while the solve goes on; the caller of
+    // stream_progress has just synchronised the solve's stream, so those rows are complete in the staging arrays
+    size_t copied = 0;
+    auto copy_out = [&](size_t upto) -> int {
+        if (upto <= copied) return 0;
+        for (int k = 0; k < 7; ++k)
+            if (host[k])
+                CUDA_OK(cudaMemcpyAsync((char*)host[k] + copied * row[k], (char*)h->so_buf[k] + copied * row[k], (upto - copied) * row[k],
+                                        cudaMemcpyDeviceToHost, h->s_copy));
+        copied = upto;
+        return 0;
+    };
+    h->stream_progress = [&](int prefix) -> int { return copy_out((size_t)std::max(prefix, 0) > n ? n : (size_t)std::max(prefix, 0)); };
+    auto dev = [&](int k) { return host[k] ? h->so_buf[k] : nullptr; };
+    int rc = trajopt_solve_stream(h, h->so_x0, n_problems, us0_bytes ? h->s_us0 : nullptr, (double*)dev(0), (double*)dev(1),
+                                  (double*)dev(2), (int32_t*)dev(3), (int32_t*)dev(4), (double*)dev(5), (double*)dev(6), stream);
+    h->stream_progress = nullptr;
+    if (rc) return rc;
+    if ((rc = copy_out(n))) return rc;
+    CUDA_OK(cudaStreamSynchronize(h->s_copy));
+    return 0;
 }
 
 int trajopt_solve_host(trajopt_handle* h, const double* h_x0, const double* h_us_init, int us_mode, double* h_xs,

@@ -9,6 +9,7 @@
 #include <cstring>
 #include <new>
 #include <vector>
+#include <functional>
 
 #include "kernels_fwd.cuh"
 #include "debug.cuh"
@@ -44,6 +45,12 @@ struct trajopt_handle {
     cudaEvent_t ev_join = nullptr;
     bool lin_ready = false;
     bool streaming = false;      // inside trajopt_solve_stream
+    std::function<int(int)> stream_progress;   // called once per iteration with the completed prefix of problem ids
+    cudaStream_t s_copy = nullptr;              // trajopt_solve_stream_host: device -> host copies beside the solve
+    void* so_buf[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // its device staging (xs, us, J, iters, status, grad, defect)
+    size_t so_bytes[7] = {0, 0, 0, 0, 0, 0, 0};
+    double* so_x0 = nullptr;
+    size_t so_x0_bytes = 0;
     int it = 0;              // next inner iteration
     bool inner_done = true;  // the inner loop of the current fit() / AL outer iteration has ended
     int al_outer = 0;        // AL outer iterations completed

@@ -15,6 +15,7 @@
 //   k_stream_admit     free slots <- next problems of the queue: x0, regulariser / counters reset, `fresh` flag
 //   k_init_ms/_ss      initial guess of the fresh slots (same kernels as trajopt_begin, masked)
 //   k_linearize        of the fresh slots when the records of the others are already current (overlapped rollout)
+//   (host variant)     rows of the completed prefix of problem ids are copied to the host on a side stream meanwhile
 //   inner_iteration    unchanged kernels; the iteration index of a slot is its own `iters` (it < 0 convention)
 // The host reads the three counters once per iteration (the same single synchronisation trajopt_iterate has).
 #pragma once
@@ -36,21 +37,21 @@ static __global__ void k_stream_clear(const Params prm, Work w) {
 
 static __global__ void __launch_bounds__(kCollectThreads) k_stream_collect(const Params prm, Work w) {
     __shared__ int s_free[kCollectThreads], s_done[kCollectThreads];
-    __shared__ int s_run;
+    __shared__ int s_run, s_min;
     const int t = threadIdx.x;
     const int per = (prm.B + kCollectThreads - 1) / kCollectThreads;
     const int lo = t * per, hi = min(lo + per, prm.B);
-    if (t == 0) s_run = 0;
-    int nf = 0, nd = 0, nr = 0;
+    if (t == 0) { s_run = 0; s_min = 0x7fffffff; }
+    int nf = 0, nd = 0, nr = 0, lowest = 0x7fffffff;
     for (int b = lo; b < hi; ++b) {
-        if (w.status[b] == TRAJOPT_RUNNING) { ++nr; continue; }
+        if (w.status[b] == TRAJOPT_RUNNING) { ++nr; lowest = min(lowest, w.slot_id[b]); continue; }
         ++nf;
         if (w.slot_id[b] >= 0) ++nd;
     }
     s_free[t] = nf;
     s_done[t] = nd;
     __syncthreads();
-    if (nr) atomicAdd(&s_run, nr);
+    if (nr) { atomicAdd(&s_run, nr); atomicMin(&s_min, lowest); }
     for (int off = 1; off < kCollectThreads; off <<= 1) {   // inclusive scans
         const int a = (t >= off) ? s_free[t - off] : 0, c = (t >= off) ? s_done[t - off] : 0;
         __syncthreads();
@@ -69,7 +70,7 @@ static __global__ void __launch_bounds__(kCollectThreads) k_stream_collect(const
         w.scnt[1] = s_done[t];
     }
     __syncthreads();
-    if (t == 0) w.scnt[2] = s_run;
+    if (t == 0) { w.scnt[2] = s_run; w.scnt[3] = s_min; }   // [3]: lowest problem id still running
 }
 
 // rows [stage][field] of the finished problems -> out[id][stage][field]
@@ -179,6 +180,9 @@ int solve_stream_impl(trajopt_handle* h, const double* d_x0, int M, double* d_xs
         CUDA_OK(cudaStreamSynchronize(s));
         const int n_free = h->h_counters[0], n_run = h->h_counters[2];
         const int admitted = std::min(n_free, M - q_head);
+        if (h->stream_progress) {   // every problem below this id has been exported (trajopt_solve_stream_host copies them out)
+            if ((rc = h->stream_progress(std::min(h->h_counters[3], q_head)))) return rc;
+        }
         q_head += admitted;
         if (q_head >= M && n_run + admitted == 0) return 0;   // queue empty, nothing was running: everything is exported
     }

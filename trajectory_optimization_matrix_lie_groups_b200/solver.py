@@ -238,6 +238,34 @@ class BatchSolver:
                                        _stream(self.device)))
         return out
 
+    def solve_stream_host(self, x0, us_init=None, trajectories=True, out=None):
+        """`solve_stream` through HOST buffers (NumPy, ideally pinned): (M, NS) in, M rows out, copies overlapped."""
+        N = self.N
+        x0 = np.ascontiguousarray(x0, dtype=np.float64)
+        if x0.ndim != 2 or x0.shape[1] != self.NS:
+            raise ValueError(f"x0 must be (M, {self.NS})")
+        M = x0.shape[0]
+        us_p = C.c_void_p(0)
+        if us_init is not None:
+            us_init = np.ascontiguousarray(us_init, dtype=np.float64)
+            if us_init.shape != (N, self.NU):
+                raise ValueError(f"us_init must be {(N, self.NU)}")
+            us_p = us_init.ctypes.data_as(C.c_void_p)
+        if out is None:
+            out = {"J": np.empty(M), "iters": np.empty(M, dtype=np.int32), "status": np.empty(M, dtype=np.int32),
+                   "grad": np.empty(M), "defect": np.empty(M),
+                   "xs": np.empty((M, N + 1, self.NS)) if trajectories else None,
+                   "us": np.empty((M, N, self.NU)) if trajectories else None}
+        if M == 0:
+            return out
+
+        def hp(a):
+            return C.c_void_p(0) if a is None else a.ctypes.data_as(C.c_void_p)
+        check(lib.trajopt_solve_stream_host(self._h, x0.ctypes.data_as(C.c_void_p), M, us_p, hp(out["xs"]), hp(out["us"]),
+                                            hp(out["J"]), hp(out["iters"]), hp(out["status"]), hp(out["grad"]),
+                                            hp(out["defect"]), _stream(self.device)))
+        return out
+
     def solve_host(self, x0, us_init=None, trajectories=True, out=None):
         """Same through HOST buffers (NumPy, ideally pinned): H2D, solve, D2H inside one call."""
         B, N = self.B, self.N
