@@ -462,7 +462,7 @@ def main():
     ap.add_argument("--no-traj", action="store_true", help="e2e leg returns only the per-problem summaries")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--inflight", type=int, default=0,
-                    help="batches in flight per GPU (1 = strictly one after the other; 0 = auto: 2, or 8 for batches <= 2048)")
+                    help="batches in flight per GPU (1 = strictly one after the other; 0 = auto: 3, or 8 for batches <= 2048)")
     ap.add_argument("--schedule", default="pipelined", choices=["stream", "pipelined"],
                     help="pipelined (default): whole batches, --inflight of them at a time; stream: continuous batching, the K "
                          "steps' problems are one queue through batch_per_gpu slots (trajopt_solve_stream) — measured slower on "
@@ -472,7 +472,7 @@ def main():
     if args.batch is None:
         args.batch = {1: 1, 2: 1024, 3: 16384, 4: 2048, 5: 131072}[args.config]
     if args.inflight <= 0:
-        args.inflight = 2 if args.batch > 2048 else 8
+        args.inflight = 3 if args.batch > 2048 else 8
     if args.schedule == "stream" and args.config == 4:
         raise SystemExit("--schedule stream: the augmented-Lagrangian method is solved per batch (use pipelined)")
     if args.impl == "reference":
