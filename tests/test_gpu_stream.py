@@ -61,3 +61,27 @@ def test_stream_rejects_what_belongs_to_a_batch():
     s.set_horizons(None)
     assert s.solve_stream(gc.perturbed_x0(x0, 16))["J"].shape == (16,)
     assert s.solve_stream(np.zeros((0, s.NS)))["J"].shape == (0,)
+
+
+@pytest.mark.parametrize("pinned", [True, False])
+def test_solve_host_sends_finished_rows_early(pinned):
+    """trajopt_solve_host copies the rows of the problems that have stopped while the stragglers still iterate, and
+    the stragglers' rows at the end (by a kernel writing pinned memory, or run by run for pageable memory): same bytes
+    as the device path either way."""
+    g = problems.load_golden("se3_n120")
+    B = 96
+    s, x0, N = gc.make_solver(g, "ms", B, horizon=40, max_iters=60, tol_grad_norm=1e-6)
+    X0 = gc.perturbed_x0(x0, B, scale=0.01)
+    X0[5::8] = gc.perturbed_x0(x0, B, seed=7, scale=0.5)[5::8]      # one straggler in eight
+    ref = s.solve(X0)
+    it = ref["iters"].cpu().numpy()
+    still = [int((it > k).sum()) for k in range(int(it.max()))]
+    assert any(0 < n <= B // 4 for n in still), still                   # some iteration ends with 0 < running <= B/4: early path
+    out = None
+    if pinned:
+        mk = lambda *shape, dtype=torch.float64: torch.full(shape, -7, dtype=dtype).pin_memory().numpy()   # noqa: E731
+        out = {"J": mk(B), "iters": mk(B, dtype=torch.int32), "status": mk(B, dtype=torch.int32), "grad": mk(B), "defect": mk(B),
+               "xs": mk(B, N + 1, s.NS), "us": mk(B, N, s.NU)}
+    host = s.solve_host(X0, out=out)
+    for k in ("iters", "status", "J", "grad", "defect", "us", "xs"):
+        assert np.array_equal(host[k], ref[k].cpu().numpy()), k

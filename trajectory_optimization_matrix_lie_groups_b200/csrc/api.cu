@@ -100,7 +100,10 @@ int trajopt_create(int kind, int method, int N, int B, int device, trajopt_handl
 #undef A_
     w.ref = h->d_ref;
     w.ref_batch = nullptr;
-    if (!rc && cudaMallocHost((void**)&h->h_counters, 4 * sizeof(int)) != cudaSuccess) rc = fail(TRAJOPT_E_CUDA, "cudaMallocHost failed");
+    if (!rc && cudaHostAlloc((void**)&h->h_counters, 4 * sizeof(int), cudaHostAllocMapped) != cudaSuccess) rc = fail(TRAJOPT_E_CUDA, "cudaHostAlloc failed");
+    if (!rc && cudaHostGetDevicePointer((void**)&h->h_counters_dev, h->h_counters, 0) != cudaSuccess) rc = fail(TRAJOPT_E_CUDA, "cudaHostGetDevicePointer failed");
+    if (!rc && cudaHostAlloc((void**)&h->h_ints, (size_t)Bp * sizeof(int), cudaHostAllocMapped) != cudaSuccess) rc = fail(TRAJOPT_E_CUDA, "cudaHostAlloc failed");
+    if (!rc && cudaHostGetDevicePointer((void**)&h->h_ints_dev, h->h_ints, 0) != cudaSuccess) rc = fail(TRAJOPT_E_CUDA, "cudaHostGetDevicePointer failed");
     if (!rc && (cudaEventCreate(&h->ev[0]) != cudaSuccess || cudaEventCreate(&h->ev[1]) != cudaSuccess))
         rc = fail(TRAJOPT_E_CUDA, "cudaEventCreate failed");
     if (!rc && method != TRAJOPT_SS) {
@@ -131,12 +134,14 @@ int trajopt_destroy(trajopt_handle* h) {
     if (h->d_perm) cudaFree(h->d_perm);
     if (h->d_scratch) cudaFree(h->d_scratch);
     if (h->h_counters) cudaFreeHost(h->h_counters);
+    if (h->h_ints) cudaFreeHost(h->h_ints);
     if (h->ev[0]) cudaEventDestroy(h->ev[0]);
     if (h->ev[1]) cudaEventDestroy(h->ev[1]);
     for (cudaEvent_t e : h->ev_chunk) if (e) cudaEventDestroy(e);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->s2) cudaStreamDestroy(h->s2);
     if (h->s_copy) cudaStreamDestroy(h->s_copy);
+    for (cudaEvent_t e : h->ev_host) if (e) cudaEventDestroy(e);
     for (void* p : h->so_buf) if (p) cudaFree(p);
     if (h->so_x0) cudaFree(h->so_x0);
     delete h;
@@ -463,6 +468,12 @@ int trajopt_solve_stream_host(trajopt_handle* h, const double* h_x0, int64_t n_p
     return 0;
 }
 
+// TRAJOPT_HOST_EARLY_COPY=0: copy everything at the end of the solve (A/B measurements)
+static bool host_early_copy() {
+    static const bool v = [] { const char* e = getenv("TRAJOPT_HOST_EARLY_COPY"); return !e || atoi(e) != 0; }();
+    return v;
+}
+
 int trajopt_solve_host(trajopt_handle* h, const double* h_x0, const double* h_us_init, int us_mode, double* h_xs,
                        double* h_us, double* h_J, int32_t* h_iters, int32_t* h_status, double* h_grad, double* h_defect,
                        void* stream) {
@@ -491,11 +502,74 @@ int trajopt_solve_host(trajopt_handle* h, const double* h_x0, const double* h_us
     }
     CUDA_OK(cudaMemcpyAsync(h->s_x0, h_x0, B * h->NS * 8, cudaMemcpyHostToDevice, s));
     if (us0_bytes) CUDA_OK(cudaMemcpyAsync(h->s_us0, h_us_init, us0_bytes, cudaMemcpyHostToDevice, s));
-    int rc = trajopt_solve(h, h->s_x0, us0_bytes ? h->s_us0 : nullptr, us_mode, h_xs ? h->s_xs : nullptr,
-                           h_us ? h->s_us : nullptr, h->s_J, h->s_iters, h->s_status, h->s_grad, h->s_def, stream);
+    // The solve, with the trajectories of the problems that have already stopped sent home EARLY: once three quarters
+    // of the batch have finished, their rows are final; everything is exported to the staging arrays and copied to the
+    // host on a side stream while the remaining iterations run (on the headline workload: 90 % of 2.4 GB behind the
+    // last seven iterations).  At the end only the rows of the late problems are copied again.
+    int rc = trajopt_begin(h, h->s_x0, us0_bytes ? h->s_us0 : nullptr, us_mode, stream);
     if (rc) return rc;
-    if (h_xs) CUDA_OK(cudaMemcpyAsync(h_xs, h->s_xs, B * (N + 1) * h->NS * 8, cudaMemcpyDeviceToHost, s));
-    if (h_us) CUDA_OK(cudaMemcpyAsync(h_us, h->s_us, B * N * h->NU * 8, cudaMemcpyDeviceToHost, s));
+    const int units = (h->method == TRAJOPT_AL_MS) ? h->user.n_al_iters : h->prm.max_iters + 1;
+    const bool can_early = (h_xs || h_us) && h->method != TRAJOPT_AL_MS && host_early_copy();
+    bool early = false;
+    std::vector<int32_t> snap;
+    if (can_early) {
+        if (!h->s_copy) CUDA_OK(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
+        if (!h->ev_host[0]) {
+            CUDA_OK(cudaEventCreateWithFlags(&h->ev_host[0], cudaEventDisableTiming));
+            CUDA_OK(cudaEventCreateWithFlags(&h->ev_host[1], cudaEventDisableTiming));
+        }
+    }
+    int active = 1;
+    for (int u = 0; u < units && active != 0; ++u) {
+        if ((rc = trajopt_iterate(h, 1, &active, stream))) return rc;
+        if (can_early && !early && active > 0 && (size_t)active * 4 <= B) {
+            if ((rc = trajopt_export(h, h_xs ? h->s_xs : nullptr, h_us ? h->s_us : nullptr, nullptr, nullptr, h->s_status, nullptr,
+                                     nullptr, stream)))
+                return rc;
+            LAUNCH(k_ints_to_host, blocks_for((int)B, 256), 256, 0, s, (const int*)h->s_status, (volatile int*)h->h_ints_dev, (int)B);
+            CUDA_OK(cudaEventRecord(h->ev_host[0], s));
+            CUDA_OK(cudaStreamWaitEvent(h->s_copy, h->ev_host[0], 0));
+            if (h_xs) CUDA_OK(cudaMemcpyAsync(h_xs, h->s_xs, B * (N + 1) * h->NS * 8, cudaMemcpyDeviceToHost, h->s_copy));
+            if (h_us) CUDA_OK(cudaMemcpyAsync(h_us, h->s_us, B * N * h->NU * 8, cudaMemcpyDeviceToHost, h->s_copy));
+            CUDA_OK(cudaEventRecord(h->ev_host[1], h->s_copy));
+            CUDA_OK(cudaStreamSynchronize(s));
+            snap.assign(h->h_ints, h->h_ints + B);
+            early = true;
+        }
+    }
+    if (early) CUDA_OK(cudaStreamWaitEvent(s, h->ev_host[1], 0));   // the staging arrays are about to be rewritten
+    if ((rc = trajopt_export(h, h_xs ? h->s_xs : nullptr, h_us ? h->s_us : nullptr, h->s_J, h->s_iters, h->s_status, h->s_grad,
+                             h->s_def, stream)))
+        return rc;
+    if (!early) {
+        if (h_xs) CUDA_OK(cudaMemcpyAsync(h_xs, h->s_xs, B * (N + 1) * h->NS * 8, cudaMemcpyDeviceToHost, s));
+        if (h_us) CUDA_OK(cudaMemcpyAsync(h_us, h->s_us, B * N * h->NU * 8, cudaMemcpyDeviceToHost, s));
+    } else {
+        // the problems that were still running at the early export: their rows go again
+        std::vector<int> late;
+        for (size_t b = 0; b < B; ++b)
+            if ((snap[b] & 15) == TRAJOPT_RUNNING) late.push_back((int)b);
+        void *dx = nullptr, *du = nullptr;
+        const bool mapped = (!h_xs || cudaHostGetDevicePointer(&dx, h_xs, 0) == cudaSuccess) &&
+                            (!h_us || cudaHostGetDevicePointer(&du, h_us, 0) == cudaSuccess);
+        if (!mapped) (void)cudaGetLastError();
+        if (mapped && !late.empty()) {          // pinned host arrays: the kernel writes the rows over PCIe itself
+            if (!h->d_perm) CUDA_OK(cudaMalloc((void**)&h->d_perm, (size_t)h->Bp * sizeof(int)));
+            CUDA_OK(cudaMemcpyAsync(h->d_perm, late.data(), late.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+            if (h_xs) LAUNCH(k_rows_to_host, (unsigned)late.size(), 256, 0, s, (const int*)h->d_perm, (size_t)(N + 1) * h->NS, (const double*)h->s_xs, (double*)dx);
+            if (h_us) LAUNCH(k_rows_to_host, (unsigned)late.size(), 256, 0, s, (const int*)h->d_perm, (size_t)N * h->NU, (const double*)h->s_us, (double*)du);
+        } else {
+            const size_t rx = (N + 1) * h->NS * 8, ru = N * h->NU * 8;
+            for (size_t i = 0; i < late.size();) {      // pageable host arrays: one copy per run of consecutive rows
+                size_t e = i + 1;
+                while (e < late.size() && late[e] == late[e - 1] + 1) ++e;
+                const size_t b = (size_t)late[i], n = e - i;
+                if (h_xs) CUDA_OK(cudaMemcpyAsync((char*)h_xs + b * rx, (char*)h->s_xs + b * rx, n * rx, cudaMemcpyDeviceToHost, s));
+                if (h_us) CUDA_OK(cudaMemcpyAsync((char*)h_us + b * ru, (char*)h->s_us + b * ru, n * ru, cudaMemcpyDeviceToHost, s));
+                i = e;
+            }
+        }
+    }
     if (h_J) CUDA_OK(cudaMemcpyAsync(h_J, h->s_J, B * 8, cudaMemcpyDeviceToHost, s));
     if (h_grad) CUDA_OK(cudaMemcpyAsync(h_grad, h->s_grad, B * 8, cudaMemcpyDeviceToHost, s));
     if (h_defect) CUDA_OK(cudaMemcpyAsync(h_defect, h->s_def, B * 8, cudaMemcpyDeviceToHost, s));

@@ -46,7 +46,8 @@ struct trajopt_handle {
     bool lin_ready = false;
     bool streaming = false;      // inside trajopt_solve_stream
     std::function<int(int)> stream_progress;   // called once per iteration with the completed prefix of problem ids
-    cudaStream_t s_copy = nullptr;              // trajopt_solve_stream_host: device -> host copies beside the solve
+    cudaStream_t s_copy = nullptr;              // trajopt_solve_host / _stream_host: device -> host copies beside the solve
+    cudaEvent_t ev_host[2] = {nullptr, nullptr};
     void* so_buf[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // its device staging (xs, us, J, iters, status, grad, defect)
     size_t so_bytes[7] = {0, 0, 0, 0, 0, 0, 0};
     double* so_x0 = nullptr;
@@ -66,7 +67,10 @@ struct trajopt_handle {
     double* d_ref = nullptr;
     double* d_ref_batch = nullptr;   // per-problem references, allocated on first use
     double* d_dweight = nullptr;
-    int* h_counters = nullptr;   // pinned
+    int* h_counters = nullptr;   // pinned, written by k_publish4 through its device alias
+    int* h_counters_dev = nullptr;
+    int* h_ints = nullptr;       // [Bp] pinned + mapped: status snapshots (compaction, early host copies), same reason
+    int* h_ints_dev = nullptr;
     // host staging for trajopt_solve_host
     double *s_x0 = nullptr, *s_us0 = nullptr, *s_xs = nullptr, *s_us = nullptr, *s_J = nullptr, *s_grad = nullptr, *s_def = nullptr;
     int32_t *s_iters = nullptr, *s_status = nullptr;
@@ -257,7 +261,7 @@ inline int count_running(trajopt_handle* h, cudaStream_t s, int* out) {
     PhaseTimer t(h, s, PH_OTHER);
     CUDA_OK(cudaMemsetAsync(h->w.counters, 0, 4 * sizeof(int), s));
     LAUNCH(k_count_running, blocks_for(h->Bp, 128), 128, 0, s, h->prm, h->w);
-    CUDA_OK(cudaMemcpyAsync(h->h_counters, h->w.counters, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
+    LAUNCH(k_publish4, 1, 32, 0, s, (const int*)h->w.counters, (volatile int*)h->h_counters_dev);
     CUDA_OK(cudaStreamSynchronize(s));
     *out = h->h_counters[0];
     return 0;
@@ -353,9 +357,10 @@ inline int maybe_compact(trajopt_handle* h, cudaStream_t s, int act) {
     const int front = h->front;
     if ((long long)act * h->compact_ratio > front || act >= front) return 0;
     PhaseTimer t(h, s, PH_OTHER);
-    std::vector<int> st((size_t)front), src_of((size_t)front);
-    CUDA_OK(cudaMemcpyAsync(st.data(), h->w.status, (size_t)front * sizeof(int), cudaMemcpyDeviceToHost, s));
+    std::vector<int> src_of((size_t)front);
+    LAUNCH(k_ints_to_host, blocks_for(front, 256), 256, 0, s, (const int*)h->w.status, (volatile int*)h->h_ints_dev, front);
     CUDA_OK(cudaStreamSynchronize(s));
+    const int* st = h->h_ints;
     int n = 0, last_running = -1;
     for (int b = 0; b < front; ++b)
         if ((st[b] & 15) == TRAJOPT_RUNNING) { src_of[n++] = b; last_running = b; }
@@ -481,7 +486,7 @@ int iterate_impl(trajopt_handle* h, int n_iters, int* n_active_out, cudaStream_t
             CUDA_OK(cudaMemsetAsync(h->w.counters, 0, 4 * sizeof(int), s));
             LAUNCH((k_al_update<KIND>), blocks_for(h->Bp, 128), 128, 0, s, h->prm, h->w, h->user.tol_constr,
                    h->user.al_mu_scale, h->user.al_mu_max, h->al_outer);
-            CUDA_OK(cudaMemcpyAsync(h->h_counters, h->w.counters, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
+            LAUNCH(k_publish4, 1, 32, 0, s, (const int*)h->w.counters, (volatile int*)h->h_counters_dev);
             CUDA_OK(cudaStreamSynchronize(s));
         }
         remaining = h->h_counters[2];

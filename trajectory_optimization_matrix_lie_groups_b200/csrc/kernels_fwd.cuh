@@ -326,6 +326,19 @@ static __global__ void k_accept_all(const Params prm, Work w, int it_arg) {
     w.iters[b] = it + 1;
 }
 
+// Four counters -> pinned host memory, written by the kernel over PCIe.  A cudaMemcpyAsync would queue behind whatever the
+// device->host copy engine is doing — a 1.6 GB trajectory copy of this or another solver held every iteration's 16-byte
+// read-back (and with it the iteration loop) for 30 ms.
+static __global__ void k_publish4(const int* __restrict__ src, volatile int* dst_host) {
+    if (threadIdx.x < 4) dst_host[threadIdx.x] = src[threadIdx.x];
+    __threadfence_system();
+}
+
+static __global__ void k_ints_to_host(const int* __restrict__ src, volatile int* dst_host, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst_host[i] = src[i];
+}
+
 // count problems that are still running into counters[0]
 static __global__ void k_count_running(const Params prm, Work w) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -683,6 +696,14 @@ __global__ void k_export_rows(int B, int Bp, int rows, const T* src, const int* 
     const int o = orig[b];
     if (o >= B) return;
     out[(size_t)o * rows + r] = src[(size_t)r * Bp + b];
+}
+
+// rows `rows[0..n)` of a [B][row_doubles] device array -> the same rows of a HOST array (pinned, written over PCIe by
+// the kernel itself: thousands of small copy-engine transfers cost ~18 us each, these rows go at link speed)
+static __global__ void k_rows_to_host(const int* __restrict__ rows, size_t row_doubles, const double* __restrict__ src,
+                                      double* __restrict__ dst_host) {
+    const size_t base = (size_t)rows[blockIdx.x] * row_doubles;
+    for (size_t j = threadIdx.x; j < row_doubles; j += blockDim.x) dst_host[base + j] = src[base + j];
 }
 
 // Compaction (see maybe_compact in host_impl.cuh): gather the leading `front` slots of a [rows][Bp] array into their

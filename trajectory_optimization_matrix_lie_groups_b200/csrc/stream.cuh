@@ -155,7 +155,7 @@ int solve_stream_impl(trajopt_handle* h, const double* d_x0, int M, double* d_xs
         {
             PhaseTimer t(h, s, PH_OTHER);
             LAUNCH(k_stream_collect, 1, kCollectThreads, 0, s, h->prm, w);
-            CUDA_OK(cudaMemcpyAsync(h->h_counters, w.scnt, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
+            LAUNCH(k_publish4, 1, 32, 0, s, (const int*)w.scnt, (volatile int*)h->h_counters_dev);
             if (d_xs) LAUNCH(k_stream_export_traj, dim3(bg, h->N + 1), 128, 0, s, h->prm, w, h->NS, w.X[0], w.X[1], d_xs, h->N + 1);
             if (d_us) LAUNCH(k_stream_export_traj, dim3(bg, h->N), 128, 0, s, h->prm, w, h->NU, w.U[0], w.U[1], d_us, h->N);
             LAUNCH(k_stream_export_summary, bg, 128, 0, s, h->prm, w, d_J, d_iters, d_status, d_grad, d_defect);
