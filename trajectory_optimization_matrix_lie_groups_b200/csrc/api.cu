@@ -538,8 +538,14 @@ int trajopt_solve_host(trajopt_handle* h, const double* h_x0, const double* h_us
         }
     }
     if (early) CUDA_OK(cudaStreamWaitEvent(s, h->ev_host[1], 0));   // the staging arrays are about to be rewritten
-    if ((rc = trajopt_export(h, h_xs ? h->s_xs : nullptr, h_us ? h->s_us : nullptr, h->s_J, h->s_iters, h->s_status, h->s_grad,
-                             h->s_def, stream)))
+    if (early) {   // only the stragglers' rows are new; s_status still holds the snapshot of the early export
+        const int bg = blocks_for(h->Bp, 128);
+        const Work& w = h->w;
+        if (h_xs) LAUNCH(k_export_traj_late, dim3(bg, h->N + 1), 128, 0, s, h->B, h->Bp, h->NS, w.X[0], w.X[1], w.sel, (const int*)w.orig, (const int*)h->s_status, h->s_xs, h->N + 1);
+        if (h_us) LAUNCH(k_export_traj_late, dim3(bg, h->N), 128, 0, s, h->B, h->Bp, h->NU, w.U[0], w.U[1], w.sel, (const int*)w.orig, (const int*)h->s_status, h->s_us, h->N);
+    }
+    if ((rc = trajopt_export(h, (!early && h_xs) ? h->s_xs : nullptr, (!early && h_us) ? h->s_us : nullptr, h->s_J, h->s_iters,
+                             h->s_status, h->s_grad, h->s_def, stream)))
         return rc;
     if (!early) {
         if (h_xs) CUDA_OK(cudaMemcpyAsync(h_xs, h->s_xs, B * (N + 1) * h->NS * 8, cudaMemcpyDeviceToHost, s));

@@ -687,6 +687,17 @@ static __global__ void k_export_traj(int B, int Bp, int F, const double* s0, con
     const double* src = (sel && sel[b]) ? s1 : s0;
     for (int f = 0; f < F; ++f) out[((size_t)o * nstage + stage) * F + f] = src[((size_t)stage * F + f) * Bp + b];
 }
+// the same for the problems that were still running when `snap` (status by caller index) was taken
+static __global__ void k_export_traj_late(int B, int Bp, int F, const double* s0, const double* s1, const int* sel,
+                                          const int* __restrict__ orig, const int* __restrict__ snap, double* out, int nstage) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const int stage = blockIdx.y;
+    if (b >= Bp) return;
+    const int o = orig[b];
+    if (o >= B || (snap[o] & 15) != TRAJOPT_RUNNING) return;
+    const double* src = (sel && sel[b]) ? s1 : s0;
+    for (int f = 0; f < F; ++f) out[((size_t)o * nstage + stage) * F + f] = src[((size_t)stage * F + f) * Bp + b];
+}
 // out[orig[b]][row] = src[row][b]
 template <typename T>
 __global__ void k_export_rows(int B, int Bp, int rows, const T* src, const int* __restrict__ orig, T* out) {
