@@ -121,7 +121,8 @@ def run_reference_arm(args):
         vals.append(v)
     wall = time.perf_counter() - t0
     value = statistics.mean(vals)
-    cfg = workload_config(args, None)
+    from trajectory_optimization_matrix_lie_groups_b200 import workloads
+    cfg = workload_config(args, workloads.CONFIGS[args.config](B=min(args.batch, 64)))   # same keys / values as the GPU arm's line
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1),
