@@ -677,26 +677,35 @@ __global__ void k_al_init(const Params prm, Work w, double mu0) {
 // Layout exports: SoA [stage][field][Bp] -> problem-major
 // ------------------------------------------------------------------------------------------
 // out[b][stage][f] = src_sel[b][stage][f][b]   (grid.y = stage)
+// One warp per problem and chunk of its row: element e = stage * F + f of problem (slot) b sits at src[e * Bp + b], so
+// the warp's writes are 32 consecutive doubles and its reads 32 sectors that the block's four warps (four consecutive
+// slots = one 32-byte sector) share through L1.  (One thread per (slot, stage) writing F doubles took 4-9 ms for the
+// 2.4 GB of a headline batch.)  grid = (ceil(Bp / 4), chunks of kExportChunk elements), block = 128.
+constexpr int kExportChunk = 2048;
 static __global__ void k_export_traj(int B, int Bp, int F, const double* s0, const double* s1, const int* sel,
                                      const int* __restrict__ orig, double* out, int nstage) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;   // slot
-    const int stage = blockIdx.y;
+    const int b = blockIdx.x * 4 + (threadIdx.x >> 5);      // slot
     if (b >= Bp) return;
     const int o = orig[b];                                  // the caller's problem index
     if (o >= B) return;
-    const double* src = (sel && sel[b]) ? s1 : s0;
-    for (int f = 0; f < F; ++f) out[((size_t)o * nstage + stage) * F + f] = src[((size_t)stage * F + f) * Bp + b];
+    const double* src = ((sel && sel[b]) ? s1 : s0) + b;
+    const int len = nstage * F, lane = threadIdx.x & 31;
+    const int e0 = blockIdx.y * kExportChunk, e1 = min(e0 + kExportChunk, len);
+    double* dst = out + (size_t)o * len;
+    for (int e = e0 + lane; e < e1; e += 32) dst[e] = src[(size_t)e * Bp];
 }
 // the same for the problems that were still running when `snap` (status by caller index) was taken
 static __global__ void k_export_traj_late(int B, int Bp, int F, const double* s0, const double* s1, const int* sel,
                                           const int* __restrict__ orig, const int* __restrict__ snap, double* out, int nstage) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    const int stage = blockIdx.y;
+    const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (b >= Bp) return;
     const int o = orig[b];
     if (o >= B || (snap[o] & 15) != TRAJOPT_RUNNING) return;
-    const double* src = (sel && sel[b]) ? s1 : s0;
-    for (int f = 0; f < F; ++f) out[((size_t)o * nstage + stage) * F + f] = src[((size_t)stage * F + f) * Bp + b];
+    const double* src = ((sel && sel[b]) ? s1 : s0) + b;
+    const int len = nstage * F, lane = threadIdx.x & 31;
+    const int e0 = blockIdx.y * kExportChunk, e1 = min(e0 + kExportChunk, len);
+    double* dst = out + (size_t)o * len;
+    for (int e = e0 + lane; e < e1; e += 32) dst[e] = src[(size_t)e * Bp];
 }
 // out[orig[b]][row] = src[row][b]
 template <typename T>
