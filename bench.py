@@ -78,6 +78,9 @@ def cpu_sample(config, n_iters, iters_per_solve, cores=None):
 
     Returns (solves_per_second extrapolated to whole solves, cores, description)."""
     import multiprocessing as mp
+    # one single-threaded process per core (the reference's joblib sweep); BLAS pools on top of that only oversubscribe
+    for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[var] = "1"
     cores = cores or int(os.environ.get("TRAJOPT_BENCH_CORES", "0")) or len(os.sched_getaffinity(0))
     batch = max(cores, 12)
     jobs = [(config, b, n_iters, batch) for b in range(cores)]
