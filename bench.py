@@ -337,6 +337,8 @@ def run_gpu_arm(args):
     Jfin = out["J"].cpu().numpy()
 
     # ---- end to end through the host-buffer C-ABI call --------------------------------------
+    if args.e2e_inflight > 0 and not stream_mode:
+        pipe.active_depth = min(args.e2e_inflight, depth)
     run_steps(min(depth, 2), True)
     barrier()
     t0 = time.perf_counter()
@@ -353,6 +355,7 @@ def run_gpu_arm(args):
     d2h = sum(v.nbytes for v in out_np.values() if v is not None)
     assert np.array_equal(out_np["iters"], iters), "host-buffer path and device path disagree"
 
+    pipe.active_depth = depth
     # ---- one batch alone (no overlap): latency of a step, and the serial throughput for comparison ----
     barrier()
     s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -467,6 +470,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--inflight", type=int, default=0,
                     help="batches in flight per GPU (1 = strictly one after the other; 0 = auto: 3, or 8 for batches <= 2048)")
+    ap.add_argument("--e2e-inflight", type=int, default=0,
+                    help="batches in flight in the host-buffer (e2e) leg; 0 = same as --inflight")
     ap.add_argument("--schedule", default="pipelined", choices=["stream", "pipelined"],
                     help="pipelined (default): whole batches, --inflight of them at a time; stream: continuous batching, the K "
                          "steps' problems are one queue through batch_per_gpu slots (trajopt_solve_stream) — measured slower on "

@@ -28,6 +28,7 @@ class PipelinedSolver:
         self.solvers = [make_solver() for _ in range(depth)]
         self.streams = [torch.cuda.Stream(device=self.device) for _ in range(depth)]
         self.pools = [ThreadPoolExecutor(max_workers=1, thread_name_prefix=f"trajopt-lane{i}") for i in range(depth)]
+        self.active_depth = depth     # lanes in use (<= depth): submit() goes round-robin over the first `active_depth` lanes
         self._next = 0
         self._lock = threading.Lock()
 
@@ -44,8 +45,8 @@ class PipelinedSolver:
         caller drops them (device results are fresh tensors; host results are `out` or fresh arrays).
         """
         with self._lock:
-            lane = self._next
-            self._next = (self._next + 1) % self.depth
+            lane = self._next % max(1, min(self.active_depth, self.depth))
+            self._next = (lane + 1) % max(1, min(self.active_depth, self.depth))
         if host:
             fn = lambda s, *a, **k: s.solve_host(*a, **k)      # noqa: E731
             return self.pools[lane].submit(self._run, lane, fn, (x0, us_init), dict(trajectories=trajectories, out=out))
