@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(kB3Threads * G, 4 / G) k_backward3(const Param
     using D = Dims<KIND>;
     using LR = LinRec<KIND>;
     using SM = B3Smem<KIND>;
-    constexpr int NX = D::NX, NP = D::NP, NU = D::NU, NV = NX - NP, F = LR::LEN, NYC = SM::NYC;
+    constexpr int NX = D::NX, NP = D::NP, NU = D::NU, NV = NX - NP, F = LR::LEN;
     extern __shared__ __align__(128) double sm_cta[];
     const int lane = threadIdx.x & 31;
     const int warp = (threadIdx.x >> 5) & 1;

@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(kBlock) k_forward_ms_full(const Params prm, Wo
     using D = Dims<KIND>;
     using LR = LinRec<KIND>;
     using FS = FwdSmem<KIND>;
-    constexpr int NX = D::NX, NP = D::NP, NU = D::NU, NV = NX - NP, F = LR::LEN, NS = D::NS;
+    constexpr int NX = D::NX, NP = D::NP, NU = D::NU, NV = NX - NP, F = LR::LEN;
     constexpr int GL = GPre<KIND>::LEN, GP = GPre<KIND>::NPOSE;
     extern __shared__ __align__(128) double fsm[];
     const int lane = threadIdx.x;
