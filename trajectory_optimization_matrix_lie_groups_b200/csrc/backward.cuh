@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(LPW) k_backward(const Params prm, Work w, int 
 #pragma unroll
                 for (int c = a; c < NU; ++c) {
                     double s = 2.0 * prm.R[a * NU + c];
-                    if (a == c) s += rec[(size_t)(LR::LUU_OFF + a) * kRecStride];
+                    if (a == c && prm.has_constraints) s += rec[(size_t)(LR::LUU_OFF + a) * kRecStride];
 #pragma unroll
                     for (int r = 0; r < NV; ++r)
                         if (bv_nz<KIND>(r, a)) s = fma(Bv.get(r, a), T[r * NU + c], s);

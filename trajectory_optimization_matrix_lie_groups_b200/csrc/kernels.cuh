@@ -487,9 +487,10 @@ __global__ void __launch_bounds__(128, 3) k_linearize(const Params prm, Work w, 
             for (int j = 0; j < NU; ++j) lu[j] += lu_add[j];
         }
 #pragma unroll
-        for (int j = 0; j < NU; ++j) {
-            out[lsoa(stage, LR::LU_OFF + j, F, prm.N + 1, b)] = lu[j];
-            out[lsoa(stage, LR::LUU_OFF + j, F, prm.N + 1, b)] = luu_add[j];
+        for (int j = 0; j < NU; ++j) out[lsoa(stage, LR::LU_OFF + j, F, prm.N + 1, b)] = lu[j];
+        if (prm.has_constraints) {   // only the AL cost adds to l_uu, and only then does the sweep read these rows
+#pragma unroll
+            for (int j = 0; j < NU; ++j) out[lsoa(stage, LR::LUU_OFF + j, F, prm.N + 1, b)] = luu_add[j];
         }
         // dynamics Jacobian
         double rec[LR::A_LEN];

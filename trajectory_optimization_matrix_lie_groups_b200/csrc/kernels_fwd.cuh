@@ -452,7 +452,7 @@ __global__ void __launch_bounds__(kBlock) k_ms_expected(const Params prm, Work w
 #pragma unroll
             for (int c = 0; c < NU; ++c) {
                 double l = 2.0 * prm.R[r * NU + c];
-                if (r == c) l += lin[lsoa(i, LR::LUU_OFF + r, F, N + 1, b)];
+                if (r == c && prm.has_constraints) l += lin[lsoa(i, LR::LUU_OFF + r, F, N + 1, b)];
                 f2 += du[r] * l * du[c];
             }
         c1 += f1;
