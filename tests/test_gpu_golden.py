@@ -124,3 +124,17 @@ def test_host_buffer_call_equals_device_call():
     host = s.solve_host(X0)
     for k in ("J", "iters", "status", "grad", "defect", "xs", "us"):
         assert np.array_equal(dev[k].cpu().numpy(), host[k]), k
+
+
+def test_overlapped_rollout_path_at_small_sizes():
+    """The rollout-beside-linearisation path is reserved for batches of >= 4096 problems; here the golden replays run
+    through it (TRAJOPT_OVERLAP_MIN_BATCH=0, read once per process: hence the subprocess)."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, TRAJOPT_OVERLAP_MIN_BATCH="0")
+    here = os.path.dirname(os.path.abspath(__file__))
+    proc = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", "-k", "not overlapped_rollout_path",
+                           os.path.join(here, "test_gpu_golden.py"), os.path.join(here, "test_gpu_compaction.py")],
+                          env=env, capture_output=True, text=True, timeout=900, cwd=os.path.dirname(here))
+    assert proc.returncode == 0, proc.stdout[-2000:] + proc.stderr[-1000:]

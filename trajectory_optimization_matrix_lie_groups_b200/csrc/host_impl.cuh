@@ -165,11 +165,23 @@ int run_linearize(trajopt_handle* h, cudaStream_t s) {
 // Small batches are launch bound (1024 SO3 problems: 17 launches per iteration instead of 4 cost 3.8x in throughput with
 // eight batches in flight); the overlap is for batches that fill the device.
 constexpr int kOverlapMinBatch = 4096;
+// TRAJOPT_OVERLAP_MIN_BATCH overrides it (tests run the overlapped path at small sizes through it)
+inline int overlap_min_batch() {
+    static const int v = [] { const char* e = getenv("TRAJOPT_OVERLAP_MIN_BATCH"); return e ? atoi(e) : kOverlapMinBatch; }();
+    return v;
+}
 
 // TRAJOPT_OVERLAP: chunks of the horizon for the overlapped rollout / linearisation (default 8; 0 or 1 = off)
 inline int overlap_chunks() {
     static const int v = [] { const char* e = getenv("TRAJOPT_OVERLAP"); return e ? atoi(e) : 8; }();
     return v < kMaxChunks ? v : kMaxChunks;
+}
+
+// Where the overlapped rollout is used: plain multiple shooting with one shared reference and one horizon (what the
+// full-size parity tests and the bench's serial-vs-pipelined assertion cover), batches that fill the device.
+inline bool overlap_applies(const trajopt_handle* h) {
+    return !h->profiling && h->s2 && h->method == TRAJOPT_MS && !h->var_horizons && !h->w.ref_batch && overlap_chunks() > 1 &&
+           h->N >= 8 * overlap_chunks() && h->Bp >= overlap_min_batch();
 }
 
 // The multiple-shooting full-step rollout and the linearisation of the trajectory it writes, overlapped.
@@ -313,7 +325,7 @@ int inner_iteration(trajopt_handle* h, cudaStream_t s) {
             } else {
                 if (h->prm.rollout_linear) {
                     if ((rc = run_forward<KIND, true, true, false>(h, s, 0, 1, -2, 0))) return rc;
-                } else if (!h->profiling && h->s2 && overlap_chunks() > 1 && h->N >= 8 * overlap_chunks() && h->Bp >= kOverlapMinBatch) {
+                } else if (overlap_applies(h)) {
                     if ((rc = run_forward_overlapped<KIND>(h, s, overlap_chunks()))) return rc;
                 } else {
                     PhaseTimer t(h, s, PH_FWD);
