@@ -31,8 +31,11 @@ FILES = {
     "draft1_se3_n955": ("results_benchmark_1st_draft/results_se3_tracking_benchmark.pkl", "se3"),
     "draft1_drone_n500": ("results_benchmark_1st_draft/results_drone_racing_tracking_benchmark.pkl", "drone"),
     "draft1_so3_n249": ("results_benchmark_1st_draft/results_so3_tracking_benchmark.pkl", "so3"),
-    "draft1_pendulum_n80": ("results_benchmark_1st_draft/results_pendulum_swingup_benchmark.pkl", "pendulum"),
 }
+# Not re-packed: results_benchmark_1st_draft/results_pendulum_swingup_benchmark.pkl.  It was written by an older
+# revision of the reference library (like draft1_se3_n955, which is kept for its problem definition only): today's
+# library code — and therefore the oracle — gives 41 multiple-shooting iterations against the file's 19, J_hist 8e-4
+# relative off from the first iteration on.  The 2nd-draft pendulum file (pendulum_n80) replays to 1e-15.
 
 
 def main():

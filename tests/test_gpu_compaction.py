@@ -63,3 +63,42 @@ def test_compaction_augmented_lagrangian():
         res.append(out)
     for k in res[0]:
         assert np.array_equal(res[0][k], res[1][k]), k
+
+
+def test_second_solve_on_one_handle_after_compaction_keeps_references_and_horizons():
+    """Per-problem references and horizons are persistent settings ("set before trajopt_begin"); a compaction moves them
+    with their problems, and the next solve on the same handle must find them back in the caller's order.  DISTINCT
+    references and horizons at a batch size where compaction is on by default: a mix-up changes the results."""
+    from trajectory_optimization_matrix_lie_groups_b200 import layout
+    g = problems.load_golden("se3_n120")
+    B, N = 1056, 30
+    rng = np.random.default_rng(5)
+    shift = rng.integers(0, 80, size=B)
+    q_rows_all = layout.pose_rows(False, g["prob_q_ref"])
+    q_rows = np.stack([q_rows_all[s:s + N + 1] for s in shift])
+    xi_rows = np.stack([g["prob_xi_ref"][s:s + N + 1] for s in shift])
+    horizons = rng.integers(5, N + 1, size=B).astype(np.int32)
+    X0 = None
+    res = []
+    for min_batch, ratio in ((-1, 4), (0, 1), (1024, 4)):
+        s, x0, _ = gc.make_solver(g, "ms", B, horizon=N, max_iters=40, tol_grad_norm=1e-10)
+        s.set_compaction(min_batch, ratio)
+        s.set_reference_batch(q_rows, xi_rows)
+        s.set_horizons(horizons)
+        if X0 is None:
+            X0 = gc.perturbed_x0(x0, B, scale=0.05)
+        first = _all_outputs(s, X0)
+        second = _all_outputs(s, X0)              # same handle, nothing set again
+        res.append((first, second))
+        if min_batch >= 0:                        # settings given anew after a compacted solve are taken in the caller's order
+            s.set_horizons(horizons)
+            third = _all_outputs(s, X0)
+            for k in first:
+                assert np.array_equal(first[k], third[k]), k
+        s.close()
+    ref = res[0][0]
+    assert len(np.unique(ref["iters"])) > 2
+    for first, second in res:
+        for k in ref:
+            assert np.array_equal(ref[k], first[k]), k
+            assert np.array_equal(ref[k], second[k]), ("second solve", k)

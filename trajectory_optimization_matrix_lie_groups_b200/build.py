@@ -17,8 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libtrajopt_b200.so")
 SOURCES = ["api.cu", "kind_so3.cu", "kind_se3.cu", "kind_drone.cu", "kind_rigid.cu", "kind_pend.cu"]
-HEADERS = ["common.cuh", "lie.cuh", "model.cuh", "kernels.cuh", "backward.cuh", "backward3.cuh", "kernels_fwd.cuh",
-           "debug.cuh", "host_impl.cuh", os.path.join("..", "..", "include", "trajopt_b200.h")]
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + [os.path.join("..", "..", "include", "trajopt_b200.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
 

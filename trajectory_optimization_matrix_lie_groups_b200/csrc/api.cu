@@ -66,6 +66,7 @@ int trajopt_create(int kind, int method, int N, int B, int device, trajopt_handl
     CUDA_OK(cudaGetDeviceCount(&ndev));
     if (device < 0 || device >= ndev) return fail(TRAJOPT_E_INVALID, "trajopt_create: no such CUDA device");
     DeviceGuard guard(device);
+    if (!guard.ok) return fail(TRAJOPT_E_CUDA, "trajopt_create: cannot select the CUDA device");
     trajopt_handle* h = new (std::nothrow) trajopt_handle();
     if (!h) return fail(TRAJOPT_E_INVALID, "trajopt_create: out of host memory");
     h->kind = kind; h->method = method; h->N = N; h->B = B; h->device = device;
@@ -123,8 +124,15 @@ int trajopt_create(int kind, int method, int N, int B, int device, trajopt_handl
         trajopt_destroy(h);
         return rc;
     }
-    LAUNCH(k_set_horizons, blocks_for(h->Bp, 128), 128, 0, (cudaStream_t)0, h->B, h->Bp, h->N, (const int*)nullptr, h->w.Nb);
-    CUDA_OK(cudaDeviceSynchronize());
+    rc = [&]() -> int {   // a failure here must not leak the handle
+        LAUNCH(k_set_horizons, blocks_for(h->Bp, 128), 128, 0, (cudaStream_t)0, h->B, h->Bp, h->N, (const int*)nullptr, h->w.Nb);
+        CUDA_OK(cudaDeviceSynchronize());
+        return 0;
+    }();
+    if (rc) {
+        trajopt_destroy(h);
+        return rc;
+    }
     *out = h;
     return 0;
 }
@@ -156,7 +164,8 @@ int trajopt_destroy(trajopt_handle* h) {
 int trajopt_set_params(trajopt_handle* h, const trajopt_params* p) {
     if (!h || !p) return fail(TRAJOPT_E_INVALID, "trajopt_set_params: NULL argument");
     if (!(p->dt > 0.0) || !(p->mass > 0.0)) return fail(TRAJOPT_E_INVALID, "trajopt_set_params: dt and mass must be positive");
-    if (p->max_iters < 0) return fail(TRAJOPT_E_INVALID, "trajopt_set_params: max_iters < 0");
+    if (p->max_iters < 0 || p->max_iters > 65534)   // the history exports use one grid row per iteration
+        return fail(TRAJOPT_E_INVALID, "trajopt_set_params: need 0 <= max_iters <= 65534");
     if (h->method == TRAJOPT_AL_MS && !p->has_constraints)
         return fail(TRAJOPT_E_INVALID, "trajopt_set_params: the augmented-Lagrangian method needs input bounds");
     DeviceGuard guard(h->device);
@@ -279,6 +288,7 @@ int trajopt_set_reference_batch(trajopt_handle* h, const double* d_q_ref, const 
     int rc = DISPATCH_KIND(h, set_reference_batch_impl, h, d_q_ref, d_xi_ref, (cudaStream_t)stream);
     if (rc) return rc;
     h->w.ref_batch = h->d_ref_batch;
+    h->ref_permuted = false;       // freshly written in the caller's order
     h->have_ref = true;
     h->begun = false;
     return 0;
@@ -289,6 +299,7 @@ int trajopt_set_horizons(trajopt_handle* h, const int32_t* d_N, void* stream) {
     DeviceGuard guard(h->device);
     LAUNCH(k_set_horizons, blocks_for(h->Bp, 128), 128, 0, (cudaStream_t)stream, h->B, h->Bp, h->N, (const int*)d_N, h->w.Nb);
     h->var_horizons = d_N != nullptr;
+    h->nb_permuted = false;        // freshly written in the caller's order
     h->begun = false;
     return 0;
 }
@@ -399,7 +410,9 @@ int trajopt_solve(trajopt_handle* h, const double* d_x0, const double* d_us_init
 int trajopt_solve_stream(trajopt_handle* h, const double* d_x0, int64_t n_problems, const double* d_us_init, double* d_xs,
                          double* d_us, double* d_J, int32_t* d_iters, int32_t* d_status, double* d_grad, double* d_defect,
                          void* stream) {
-    if (!h || !d_x0) return fail(TRAJOPT_E_INVALID, "trajopt_solve_stream: NULL argument");
+    if (!h) return fail(TRAJOPT_E_INVALID, "trajopt_solve_stream: NULL handle");
+    if (n_problems == 0) return 0;
+    if (!d_x0) return fail(TRAJOPT_E_INVALID, "trajopt_solve_stream: NULL argument");
     if (!h->have_params || !h->have_ref) return fail(TRAJOPT_E_STATE, "trajopt_solve_stream: set parameters and reference first");
     if (n_problems < 0 || n_problems > 0x7fffffff) return fail(TRAJOPT_E_INVALID, "trajopt_solve_stream: n_problems out of range");
     if (h->method == TRAJOPT_AL_MS) return fail(TRAJOPT_E_INVALID, "trajopt_solve_stream: the augmented-Lagrangian outer loop is per batch; use trajopt_solve");
@@ -418,7 +431,9 @@ int trajopt_solve_stream(trajopt_handle* h, const double* d_x0, int64_t n_proble
 int trajopt_solve_stream_host(trajopt_handle* h, const double* h_x0, int64_t n_problems, const double* h_us_init, double* h_xs,
                               double* h_us, double* h_J, int32_t* h_iters, int32_t* h_status, double* h_grad, double* h_defect,
                               void* stream) {
-    if (!h || !h_x0) return fail(TRAJOPT_E_INVALID, "trajopt_solve_stream_host: NULL argument");
+    if (!h) return fail(TRAJOPT_E_INVALID, "trajopt_solve_stream_host: NULL handle");
+    if (n_problems == 0) return 0;
+    if (!h_x0) return fail(TRAJOPT_E_INVALID, "trajopt_solve_stream_host: NULL argument");
     if (n_problems < 0 || n_problems > 0x7fffffff) return fail(TRAJOPT_E_INVALID, "trajopt_solve_stream_host: n_problems out of range");
     DeviceGuard guard(h->device);
     cudaStream_t s = (cudaStream_t)stream;

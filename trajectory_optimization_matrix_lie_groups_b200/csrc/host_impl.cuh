@@ -59,6 +59,9 @@ struct trajopt_handle {
     int hist_cap = -1, cand_rows = -1;
     // compaction: leading slots that may hold running problems; thresholds (see maybe_compact)
     int front = 0, compact_min_batch = 1024, compact_ratio = 4;
+    // Nb / ref_batch are settings that outlive a solve ("set before trajopt_begin"); a compaction moves them with their
+    // problems, so the next begin puts them back into the caller's order first (restore_caller_order)
+    bool nb_permuted = false, ref_permuted = false;
     int* d_perm = nullptr;
     void* d_scratch = nullptr;
     size_t scratch_bytes = 0;
@@ -368,6 +371,41 @@ int permute_array(trajopt_handle* h, cudaStream_t s, T* data, size_t rows, int f
     return 0;
 }
 
+// data[r][orig[n]] <- data[r][n] for every slot n: undoes every compaction since `orig` was the identity.  Row chunks
+// through the scratch buffer (at least 64 MiB of it), so a 4 GB per-problem reference does not need a 4 GB copy.
+template <typename T>
+int unpermute_array(trajopt_handle* h, cudaStream_t s, T* data, size_t rows) {
+    if (!data || rows == 0) return 0;
+    const size_t row_bytes = (size_t)h->Bp * sizeof(T);
+    const size_t want = std::max<size_t>(row_bytes, std::min<size_t>(rows * row_bytes, (size_t)64 << 20));
+    if (want > h->scratch_bytes) {
+        if (h->d_scratch) cudaFree(h->d_scratch);
+        h->d_scratch = nullptr;
+        h->scratch_bytes = 0;
+        CUDA_OK(cudaMalloc(&h->d_scratch, want));
+        h->scratch_bytes = want;
+    }
+    const size_t chunk = std::max<size_t>(1, h->scratch_bytes / row_bytes);
+    for (size_t r0 = 0; r0 < rows; r0 += chunk) {
+        const size_t n = std::min(chunk, rows - r0);
+        dim3 grid(blocks_for(h->Bp, 128), (unsigned)std::min<size_t>(n, 4096));
+        LAUNCH((k_unpermute_scatter<T>), grid, 128, 0, s, (int)n, h->Bp, (const T*)(data + r0 * (size_t)h->Bp), (const int*)h->w.orig,
+               (T*)h->d_scratch);
+        CUDA_OK(cudaMemcpyAsync(data + r0 * (size_t)h->Bp, h->d_scratch, n * row_bytes, cudaMemcpyDeviceToDevice, s));
+    }
+    return 0;
+}
+
+// Called before `orig` is reset to the identity (trajopt_begin, trajopt_solve_stream): the per-problem settings a
+// compaction of the previous solve moved go back to the caller's order.
+inline int restore_caller_order(trajopt_handle* h, cudaStream_t s) {
+    int rc = 0;
+    if (h->nb_permuted) rc = unpermute_array(h, s, h->w.Nb, 1);
+    if (!rc && h->ref_permuted && h->d_ref_batch) rc = unpermute_array(h, s, h->d_ref_batch, ((size_t)h->N + 1) * h->REFROW);
+    h->nb_permuted = h->ref_permuted = false;
+    return rc;
+}
+
 inline int maybe_compact(trajopt_handle* h, cudaStream_t s, int act) {
     if (h->compact_min_batch < 0 || h->Bp < h->compact_min_batch || act <= 0) return 0;
     const int front = h->front;
@@ -400,6 +438,8 @@ inline int maybe_compact(trajopt_handle* h, cudaStream_t s, int act) {
     P_(w.Jhist, mi); P_(w.gradhist, mi + 1); P_(w.defhist, mi + 1); P_(w.alphahist, mi);
     P_(h->d_dweight, 1);
     if (h->w.ref_batch) P_(h->d_ref_batch, Np1 * h->REFROW);
+    h->nb_permuted = true;
+    if (h->w.ref_batch) h->ref_permuted = true;
     if (h->method == TRAJOPT_AL_MS) {
         P_(w.lam, Np1 * 2 * h->NU); P_(w.imu, Np1 * 2 * h->NU);
         if (h->prm.has_state_bounds) { P_(w.lam_s, Np1 * 2 * (h->NX - h->NP)); P_(w.imu_s, Np1 * 2 * (h->NX - h->NP)); }
@@ -459,6 +499,10 @@ template <int KIND>
 int begin_impl(trajopt_handle* h, const double* d_x0, const double* d_us_init, int us_mode, cudaStream_t s) {
     h->w.us_init = d_us_init;
     h->w.us_mode = d_us_init ? us_mode : 0;
+    {
+        int rc0 = restore_caller_order(h, s);
+        if (rc0) return rc0;
+    }
     LAUNCH(k_identity, blocks_for(h->Bp, 128), 128, 0, s, h->Bp, h->w.orig);
     {   // histories: entries past a problem's last iteration read as zero
         const size_t Bp = (size_t)h->Bp, cap = (size_t)std::max(h->prm.max_iters, 1), cap1 = (size_t)h->prm.max_iters + 1;

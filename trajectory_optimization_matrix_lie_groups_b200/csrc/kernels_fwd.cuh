@@ -742,6 +742,14 @@ __global__ void k_permute_scatter(int rows, int Bp, int front, T* __restrict__ d
     if (n >= front) return;
     for (int r = blockIdx.y; r < rows; r += gridDim.y) data[(size_t)r * Bp + n] = scratch[(size_t)r * front + n];
 }
+// the inverse of every compaction so far: scratch[r][orig[n]] = data[r][n]  (orig is a permutation of [0, Bp))
+template <typename T>
+__global__ void k_unpermute_scatter(int rows, int Bp, const T* __restrict__ data, const int* __restrict__ orig, T* __restrict__ scratch) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= Bp) return;
+    const int o = orig[n];
+    for (int r = blockIdx.y; r < rows; r += gridDim.y) scratch[(size_t)r * Bp + o] = data[(size_t)r * Bp + n];
+}
 // per-problem horizons: out[b] = clamp(in[b], 1, N) for b < B (in == NULL: N), N for the padding slots
 static __global__ void k_set_horizons(int B, int Bp, int N, const int* __restrict__ in, int* __restrict__ out) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;

@@ -140,7 +140,9 @@ template <int KIND>
 int solve_stream_impl(trajopt_handle* h, const double* d_x0, int M, double* d_xs, double* d_us, double* d_J, int* d_iters,
                       int* d_status, double* d_grad, double* d_defect, cudaStream_t s) {
     Work& w = h->w;
+    int rc0_ = 0;
     const int bg = blocks_for(h->Bp, 128);
+    if ((rc0_ = restore_caller_order(h, s))) return rc0_;
     LAUNCH(k_identity, bg, 128, 0, s, h->Bp, w.orig);
     LAUNCH(k_stream_clear, bg, 128, 0, s, h->prm, w);
     h->it = 0;

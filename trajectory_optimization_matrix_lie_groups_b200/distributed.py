@@ -47,11 +47,15 @@ def all_gather_summaries(local, B):
         return local
     sizes = [shard_bounds(B, r, ws) for r in range(ws)]
     bmax = max(hi - lo for lo, hi in sizes)
-    pad = torch.zeros(bmax, local.shape[1], dtype=local.dtype, device=local.device)
-    pad[: local.shape[0]] = local
+    # NCCL gathers device tensors in place; a gloo job (the CPU tests, or several ranks sharing one GPU) goes through the host
+    via_host = local.is_cuda and dist.get_backend() != "nccl"
+    src = local.cpu() if via_host else local
+    pad = torch.zeros(bmax, src.shape[1], dtype=src.dtype, device=src.device)
+    pad[: src.shape[0]] = src
     parts = [torch.empty_like(pad) for _ in range(ws)]
     dist.all_gather(parts, pad)
-    return torch.cat([parts[r][: hi - lo] for r, (lo, hi) in enumerate(sizes)], dim=0)
+    table = torch.cat([parts[r][: hi - lo] for r, (lo, hi) in enumerate(sizes)], dim=0)
+    return table.to(local.device) if via_host else table
 
 
 def solve_sharded(make_solver, x0_rows, us_init=None, trajectories=False):

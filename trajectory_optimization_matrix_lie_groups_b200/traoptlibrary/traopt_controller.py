@@ -192,9 +192,13 @@ class _NativeController(BaseController):
             return sv
         if shard and ws > 1:
             lo, hi = _dist.shard_bounds(B, rank, ws)
-            out, summ, (lo, hi) = _dist.solve_sharded(lambda b: ready(b, lo), rows, us_init,
-                                                      trajectories=return_trajectories)
-            s = self._solver(hi - lo, device, **params)
+            made = []          # the solver that solved the shard: asking _solver() again would reset its state (set_params)
+
+            def make(b):
+                made.append(ready(b, lo))
+                return made[-1]
+            out, summ, (lo, hi) = _dist.solve_sharded(make, rows, us_init, trajectories=return_trajectories)
+            s = made[-1]
         else:
             lo, hi = 0, B
             s = ready(B, 0)

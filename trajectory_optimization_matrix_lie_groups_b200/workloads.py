@@ -8,9 +8,9 @@ p_x, p_y, p_z, v_x, v_y, v_z} — by a value drawn uniformly from +-10 % of the 
 half-width.  Problem 0 is the script's own unperturbed problem.  RNG: numpy default_rng(24234156),
 the seed the scripts declare (e.g. main_SE3ddp_tracking_exact.py:22).
 
-Reference trajectories come from the fixtures under tests/golden/ (re-packed result pickles of the
-reference, which embed the `q_ref`/`xi_ref` the scripts load from
-visualization/optimized_trajectories/*.npy); the reference tree itself is not needed at run time.
+Reference trajectories are package data (`data/*.npy`, in the reference's own on-disk format and under the file
+names its scripts load from visualization/optimized_trajectories/; written by scripts/make_workload_data.py and
+read with `io.load_reference_trajectory`); neither the reference tree nor the test fixtures are needed at run time.
 """
 import os
 from dataclasses import dataclass, field
@@ -19,9 +19,10 @@ import numpy as np
 from scipy.spatial.transform import Rotation
 
 from . import layout
+from .io import load_reference_trajectory
 
 SEED = 24234156
-GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+DATA_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
 
 # half-widths of the reference sweep (perturb_all_compute.py:181-194): th 30 deg, w_x 3, w_y 2, w_z 1, p 50, v 10
 SWEEP_HALF_WIDTH = np.array([30.0, 30.0, 30.0, 3.0, 2.0, 1.0, 50.0, 50.0, 50.0, 10.0, 10.0, 10.0])
@@ -69,9 +70,9 @@ class Workload:
         return s, self.x0_rows[offset:offset + B]
 
 
-def _golden(name):
-    with np.load(os.path.join(GOLDEN_DIR, name + ".npz")) as z:
-        return {k: z[k] for k in z.files}
+def _reference(name):
+    """(q_ref, xi_ref, dt) of data/<name>.npy"""
+    return load_reference_trajectory(os.path.join(DATA_DIR, name + ".npy"))
 
 
 def _rigid_J(m=1.0):
@@ -102,8 +103,7 @@ def perturb_se3(R_nom, p_nom, xi_nom, B, frac, rng):
 
 def se3_tracking_ss(B=1):
     """cfg 1: main_SE3ddp_tracking_exact.py — SE3 single shooting, N=955, dt=0.01 (script value)."""
-    g = _golden("se3_n955_r1e-5")
-    q_ref, xi_ref = g["prob_q_ref"], g["prob_xi_ref"]
+    q_ref, xi_ref, _ = _reference("path_dense_random_columns_4obj")
     Q = np.diag([10.0, 10, 10, 1, 1, 1, 1, 1, 1, 1, 1, 1])
     rng = np.random.default_rng(SEED)
     x0 = perturb_se3(q_ref[0][:3, :3], q_ref[0][:3, 3], xi_ref[0], B, 0.1, rng)
@@ -114,8 +114,7 @@ def se3_tracking_ss(B=1):
 
 def so3_tracking_ms(B=1024, method="ms"):
     """cfg 2: benchmark_SO3_tracking.py — SO3, N=249, dt=0.04, batch of perturbed initial attitudes."""
-    g = _golden("so3_n249")
-    q_ref, xi_ref = g["prob_q_ref"], g["prob_xi_ref"]
+    q_ref, xi_ref, dt = _reference("path_3dpendulum_8shape_tryout")
     Q = np.diag([10.0, 10, 10, 1, 1, 1])
     rng = np.random.default_rng(SEED)
     R_nom = Rotation.from_euler("zxy", [90.0, 10.0, 45.0], degrees=True).as_matrix()
@@ -126,15 +125,14 @@ def so3_tracking_ms(B=1024, method="ms"):
     R = np.einsum("ij,bjk->bik", R_nom, Rotation.from_rotvec(delta).as_matrix())
     w0 = 0.15 * np.ones((B, 3)) + dw
     x0 = np.concatenate((layout.rot_to_quat(R), w0), axis=1)
-    return Workload("benchmark_SO3_tracking", "so3", method, q_ref.shape[0] - 1, float(g["prob_dt"]),
+    return Workload("benchmark_SO3_tracking", "so3", method, q_ref.shape[0] - 1, float(dt),
                     np.diag([0.5, 0.7, 0.9]), Q, 1e-3 * np.eye(3), 1.5 * Q, q_ref, xi_ref, x0,
                     solver=dict(max_iters=50, tol_grad_norm=1e-8, rollout="nonlinear"))
 
 
 def se3_tracking_ms(B=16384, frac=0.1):
     """cfg 3 (headline): main_SE3ddp_tracking_exact_ms.py — SE3 multiple shooting, N=955, dt=0.004."""
-    g = _golden("se3_n955_r1e-5")
-    q_ref, xi_ref = g["prob_q_ref"], g["prob_xi_ref"]
+    q_ref, xi_ref, _ = _reference("path_dense_random_columns_4obj")
     Q = np.diag([25.0, 25, 25, 10, 10, 10, 1, 1, 1, 1, 1, 1])
     rng = np.random.default_rng(SEED)
     R_nom = Rotation.from_euler("zxy", [90.0, 10.0, 45.0], degrees=True).as_matrix()
@@ -182,16 +180,16 @@ def se3_tracking_al_ms(B=16384, frac=0.02, N=1400):
 
 def drone_racing_ms(B=1 << 20, method="ms"):
     """cfg 5: benchmark_drone_racing_tracking.py — quadrotor on SE3, N=150, small perturbation ranges."""
-    g = _golden("drone_n150")
-    q_ref, xi_ref = g["prob_q_ref"], g["prob_xi_ref"]
+    q_ref, xi_ref, _ = _reference("path_dense_random_columns_4obj")
+    q_ref, xi_ref = q_ref[:151], xi_ref[:151]          # Nsim = 150 (benchmark_drone_racing_tracking.py:56-58)
     Q = np.diag([25.0, 25, 25, 10, 10, 10, 1, 1, 1, 1, 1, 1])
     rng = np.random.default_rng(SEED)
     R_nom = Rotation.from_euler("zxy", [1e-4, 0.0, 0.0], degrees=True).as_matrix()
     # ranges of SURVEY.md section 8d cfg 5: th +-1 deg, w +-0.1, p +-0.2, v +-0.2
     frac = np.array([1.0, 1, 1, 0.1, 0.1, 0.1, 0.2, 0.2, 0.2, 0.2, 0.2, 0.2]) / SWEEP_HALF_WIDTH
     x0 = perturb_se3(R_nom, q_ref[0][:3, 3] - 0.1, 1e-3 * np.ones(6), B, frac, rng)
-    return Workload("benchmark_drone_racing_tracking", "drone", method, q_ref.shape[0] - 1, float(g["prob_dt"]),
-                    g["prob_J"], Q, 1e-5 * np.eye(4), 1.5 * Q, q_ref, xi_ref, x0,
+    return Workload("benchmark_drone_racing_tracking", "drone", method, q_ref.shape[0] - 1, 0.004,
+                    _rigid_J(), Q, 1e-5 * np.eye(4), 1.5 * Q, q_ref, xi_ref, x0,
                     solver=dict(max_iters=200, tol_grad_norm=1e-12, tol_d_norm=1e-6, rollout="nonlinear"))
 
 
