@@ -10,7 +10,12 @@ own stopping rule) of every problem of the batch.  Default workload = BASELINE.j
 global seeded batch; no collective on the data path, one NCCL all-gather of the per-problem
 summaries (J, grad, defect, iters, status) at the end of every step).
 
-`value`   device-timed (CUDA events, max over ranks) with the initial states resident in HBM.
+`value`   device-timed (CUDA events, max over ranks) with the initial states resident in HBM; the timed solves return
+          the per-problem summaries only (trajectories stay on the device; `e2e` exports and copies them).
+`strong`  BASELINE.json words the metric as "batch 16k (1-8 GPU)": ONE 16384-problem sweep split over the N ranks
+          (the reference's batch is one sweep split over its workers, visualization/perturb_all_compute.py:240-250).
+          The `strong` block reports exactly that — 16384 / N problems per GPU — device-timed, end to end, and as the
+          latency of one sweep alone; `value` stays the weak-scaling figure (16384 problems per GPU).
 `e2e`     the same solves through the host-buffer C-ABI call (`trajopt_solve_host`): pinned host x0
           copied in, trajectories and summaries copied out, all inside the timed region.
 `roofline` the backward Riccati sweep (dominant kernel): algorithmic FP64 FLOPs / measured duration
@@ -33,6 +38,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "SE3 tracking DDP solves/sec"
+# the batch BASELINE.json quotes each config on, as ONE sweep (strong scaling splits it over the ranks)
+STRONG_GLOBAL_BATCH = {1: 1, 2: 1024, 3: 16384, 4: 16384, 5: 1 << 20}
 NOMINAL_ITERS = {1: 40, 2: 16, 3: 20, 4: 60, 5: 26}   # iterations of the unperturbed problem (goldens / SURVEY.md)
 
 
@@ -212,13 +219,225 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def load_kernel_counters(kind):
+    """ncu-derived static counters of the dominant kernel (profiles/kernel_counters.json, written from a committed
+    `ncu --set full` capture by scripts/ncu_summary.py): executed FP64 thread-instructions and DRAM bytes per launch and
+    the stage-iterations that launch processed."""
+    path = os.path.join(ROOT, "profiles", "kernel_counters.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        return json.load(f).get({"se3": "k_backward3_se3", "rigid": "k_backward3_se3", "drone": "k_backward3_drone"}.get(kind, "k_backward_so3"))
+
+
+def measure_host_d2h(torch, dist, dev, world, gib=1.0, reps=3):
+    """Concurrent device->host bandwidth of the box: every rank copies `gib` GiB into pinned memory at the same time
+    (plain cudaMemcpyAsync, one large buffer).  Returns (this rank's GB/s, sum over ranks)."""
+    n = int(gib * (1 << 30)) // 8
+    src = torch.empty(n, dtype=torch.float64, device=dev)
+    dst = torch.empty(n, dtype=torch.float64).pin_memory()
+    dst.copy_(src, non_blocking=True)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        dst.copy_(src, non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    gbs = reps * n * 8 / (e0.elapsed_time(e1) * 1e-3) / 1e9
+    tot = torch.tensor([gbs], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot)
+    del src, dst
+    return gbs, float(tot.item())
+
+
+class Leg:
+    """`depth` solver lanes for batches of B problems (rows [offset, offset + B) of the workload): the device-timed and the
+    host-buffer (e2e) loops over K steps, with every buffer allocated up front."""
+
+    def __init__(self, torch, dist, wl, B, offset, depth, dev, world, want_traj, compact):
+        from trajectory_optimization_matrix_lie_groups_b200 import PipelinedSolver
+        self.torch, self.dist, self.wl, self.B, self.dev, self.world, self.want_traj = torch, dist, wl, B, dev, world, want_traj
+        self.depth = depth
+        self.x0_rows = wl.x0_rows[offset:offset + B]
+        self.pipe = PipelinedSolver(lambda: wl.make_solver(B=B, device=dev, offset=offset)[0], depth=depth, device=dev)
+        self.solver = self.pipe.solvers[0]
+        if compact:
+            mb, ratio = (int(v) for v in compact.split(","))
+            for sv in self.pipe.solvers:
+                sv.set_compaction(mb, ratio)
+        self.x0_dev = torch.as_tensor(self.x0_rows, device=dev)
+        self.x0_pin = torch.as_tensor(self.x0_rows).pin_memory()
+        self.outs = [self._pinned_out() for _ in range(depth)]      # one set of pinned result buffers per lane
+        self.gathered = [torch.empty(B, 5, dtype=torch.float64, device=dev) for _ in range(world)] if world > 1 else None
+
+    def _pinned_out(self):
+        torch, B, wl, sv = self.torch, self.B, self.wl, self.solver
+        o = {"J": torch.empty(B, dtype=torch.float64).pin_memory(), "grad": torch.empty(B, dtype=torch.float64).pin_memory(),
+             "defect": torch.empty(B, dtype=torch.float64).pin_memory(),
+             "iters": torch.empty(B, dtype=torch.int32).pin_memory(), "status": torch.empty(B, dtype=torch.int32).pin_memory(),
+             "xs": torch.empty(B, wl.N + 1, sv.NS, dtype=torch.float64).pin_memory() if self.want_traj else None,
+             "us": torch.empty(B, wl.N, sv.NU, dtype=torch.float64).pin_memory() if self.want_traj else None}
+        return o, {k: (None if v is None else v.numpy()) for k, v in o.items()}
+
+    def gather(self, out):
+        if self.world > 1:   # the one collective of the path: per-problem summaries to every rank
+            torch = self.torch
+            summ = torch.stack((out["J"], out["grad"], out["defect"], out["iters"].double(), out["status"].double()), dim=1)
+            self.dist.all_gather(self.gathered, summ)
+
+    def run_steps(self, n, host):
+        """n steps, `depth` batches in flight; steps complete (and are gathered) in submission order."""
+        futs = []
+        for k in range(n):
+            if host:
+                futs.append(self.pipe.submit(self.x0_pin.numpy(), trajectories=self.want_traj, host=True, out=self.outs[k % self.depth][1]))
+            else:
+                futs.append(self.pipe.submit(self.x0_dev, trajectories=False))
+        last = None
+        for f in futs:
+            last = f.result()
+            if not host:
+                self.gather(last)
+        return last
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize(self.dev)
+
+    def timed_device(self, steps):
+        """K steps between barriers, CUDA events, max over ranks -> (ms_total, last result)"""
+        torch = self.torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        e0.record()
+        out = self.run_steps(steps, False)      # every lane synchronises its stream before its result is handed back
+        e1.record()
+        self.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(ms, op=self.dist.ReduceOp.MAX)
+        return float(ms.item()), out
+
+    def timed_host(self, steps, e2e_depth=0):
+        """the same through trajopt_solve_host with pinned buffers: wall clock between barriers, max over ranks -> seconds"""
+        torch = self.torch
+        if e2e_depth > 0:
+            self.pipe.active_depth = min(e2e_depth, self.depth)
+        self.run_steps(min(self.depth, 2), True)
+        self.barrier()
+        t0 = time.perf_counter()
+        self.run_steps(steps, True)
+        self.barrier()
+        sec = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(sec, op=self.dist.ReduceOp.MAX)
+        self.pipe.active_depth = self.depth
+        out_np = self.outs[(steps - 1) % self.depth][1]
+        return float(sec.item()), out_np
+
+    def timed_single(self):
+        """one batch alone on the GPU -> (ms max over ranks, result)"""
+        torch = self.torch
+        self.barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        out1 = self.solver.solve(self.x0_dev, trajectories=False)
+        s1.record()
+        torch.cuda.synchronize(self.dev)
+        ms = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(ms, op=self.dist.ReduceOp.MAX)
+        return float(ms.item()), out1
+
+    def close(self):
+        self.pipe.close()
+        self.outs = []
+        self.torch.cuda.empty_cache()
+
+
+def auto_inflight(batch):
+    return 3 if batch > 2048 else 8
+
+
+def decision_window(J):
+    """Leading iterations of a cost history whose accept/stop decisions are above rounding noise (relative change >= 1e-12):
+    the span over which the parity tests assert identical decisions (tests/test_gpu_golden.py, test_gpu_configs.py)."""
+    for i in range(1, len(J)):
+        if abs(J[i] - J[i - 1]) < 1e-12 * abs(J[i]):
+            return i
+    return len(J)
+
+
+def run_stream_arm(args):
+    """--schedule stream: continuous batching (trajopt_solve_stream), kept for A/B runs; prints the base contract's keys."""
+    import numpy as np
+    import torch
+    from trajectory_optimization_matrix_lie_groups_b200 import workloads, launch_count
+    if int(os.environ.get("WORLD_SIZE", "1")) != 1:
+        raise SystemExit("--schedule stream is a single-GPU A/B mode")
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    B = args.batch
+    wl = workloads.CONFIGS[args.config](B=B)
+    solver, x0_rows = wl.make_solver(B=B, device=dev)
+    n_max = max(args.steps, args.warmup, 1)
+    x0_all_dev = torch.as_tensor(x0_rows, device=dev).repeat(n_max, 1)
+    x0_all_pin = torch.as_tensor(np.tile(x0_rows, (n_max, 1))).pin_memory()
+    M, ns, want_traj = n_max * B, args.steps, not args.no_traj
+    dev_out = {"J": torch.empty(M, dtype=torch.float64, device=dev), "grad": torch.empty(M, dtype=torch.float64, device=dev),
+               "defect": torch.empty(M, dtype=torch.float64, device=dev), "iters": torch.empty(M, dtype=torch.int32, device=dev),
+               "status": torch.empty(M, dtype=torch.int32, device=dev), "xs": None, "us": None}
+    host_t = {"J": torch.empty(ns * B, dtype=torch.float64).pin_memory(), "grad": torch.empty(ns * B, dtype=torch.float64).pin_memory(),
+              "defect": torch.empty(ns * B, dtype=torch.float64).pin_memory(),
+              "iters": torch.empty(ns * B, dtype=torch.int32).pin_memory(), "status": torch.empty(ns * B, dtype=torch.int32).pin_memory(),
+              "xs": torch.empty(ns * B, wl.N + 1, solver.NS, dtype=torch.float64).pin_memory() if want_traj else None,
+              "us": torch.empty(ns * B, wl.N, solver.NU, dtype=torch.float64).pin_memory() if want_traj else None}
+    host_out = {k: (None if v is None else v.numpy()) for k, v in host_t.items()}
+
+    def dev_steps(n):
+        o = solver.solve_stream(x0_all_dev[: n * B], trajectories=False, out={k: (None if v is None else v[: n * B]) for k, v in dev_out.items()})
+        torch.cuda.synchronize(dev)
+        return {k: (None if v is None else v[(n - 1) * B: n * B]) for k, v in o.items()}
+    if args.warmup:
+        dev_steps(args.warmup)
+    launch_count(reset=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(dev)
+    e0.record()
+    out = dev_steps(args.steps)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms_total = e0.elapsed_time(e1)
+    launches = launch_count(reset=True)
+    t0 = time.perf_counter()
+    solver.solve_stream_host(x0_all_pin.numpy()[: ns * B], trajectories=want_traj, out=host_out)
+    e2e_s = time.perf_counter() - t0
+    one = solver.solve(torch.as_tensor(x0_rows, device=dev), trajectories=False)
+    assert np.array_equal(one["iters"].cpu().numpy(), out["iters"].cpu().numpy()) and np.array_equal(one["J"].cpu().numpy(), out["J"].cpu().numpy()), \
+        "continuous batching and the batched solve disagree"
+    step_s = ms_total * 1e-3 / args.steps
+    print(json.dumps({"metric": METRIC, "value": B / step_s, "unit": "solves/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+                      "ms_per_step": 1e3 * step_s, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                      "data": "synthetic", "config": workload_config(args, wl), "gpu_launches": int(launches),
+                      "e2e": {"value": B * ns / e2e_s, "unit": "solves/s", "h2d_bytes_per_step": int(x0_rows.nbytes),
+                              "d2h_bytes_per_step": int(sum(v.nbytes for v in host_out.values() if v is not None) // ns)}}))
+    return 0
+
+
 def run_gpu_arm(args):
     import numpy as np
     import torch
     import torch.distributed as dist
-    from trajectory_optimization_matrix_lie_groups_b200 import workloads, launch_count, PipelinedSolver
+    from trajectory_optimization_matrix_lie_groups_b200 import workloads, launch_count
     from trajectory_optimization_matrix_lie_groups_b200.solver import fp64_peak_tflops
 
+    if args.schedule == "stream":
+        return run_stream_arm(args)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -233,103 +452,22 @@ def run_gpu_arm(args):
 
     B = args.batch
     wl = workloads.CONFIGS[args.config](B=B * world)
-    stream_mode = args.schedule == "stream"
-    depth = 1 if stream_mode else max(1, args.inflight)
-    x0_rows = wl.x0_rows[rank * B:rank * B + B]
-    pipe = PipelinedSolver(lambda: wl.make_solver(B=B, device=dev, offset=rank * B)[0], depth=depth, device=dev)
-    solver = pipe.solvers[0]
-    if args.compact:
-        mb, ratio = (int(v) for v in args.compact.split(","))
-        for sv in pipe.solvers:
-            sv.set_compaction(mb, ratio)
-    x0_dev = torch.as_tensor(x0_rows, device=dev)
-    x0_pin = torch.as_tensor(x0_rows).pin_memory()
+    depth = max(1, args.inflight)
     want_traj = not args.no_traj
-
-    def pinned_out():
-        o = {"J": torch.empty(B, dtype=torch.float64).pin_memory(), "grad": torch.empty(B, dtype=torch.float64).pin_memory(),
-             "defect": torch.empty(B, dtype=torch.float64).pin_memory(),
-             "iters": torch.empty(B, dtype=torch.int32).pin_memory(), "status": torch.empty(B, dtype=torch.int32).pin_memory(),
-             "xs": torch.empty(B, wl.N + 1, solver.NS, dtype=torch.float64).pin_memory() if want_traj else None,
-             "us": torch.empty(B, wl.N, solver.NU, dtype=torch.float64).pin_memory() if want_traj else None}
-        return o, {k: (None if v is None else v.numpy()) for k, v in o.items()}
-    outs = [pinned_out() for _ in range(depth)] if not stream_mode else []   # one set of pinned result buffers per lane
-    if stream_mode:
-        # continuous batching: the problems of n steps are ONE queue of n x B problems through the solver's B slots
-        n_max = max(args.steps, args.warmup, 1)
-        x0_all_dev = x0_dev.repeat(n_max, 1)
-        x0_all_pin = torch.as_tensor(np.tile(x0_rows, (n_max, 1))).pin_memory()
-        M = n_max * B
-        dev_out = {"J": torch.empty(M, dtype=torch.float64, device=dev), "grad": torch.empty(M, dtype=torch.float64, device=dev),
-                   "defect": torch.empty(M, dtype=torch.float64, device=dev), "iters": torch.empty(M, dtype=torch.int32, device=dev),
-                   "status": torch.empty(M, dtype=torch.int32, device=dev), "xs": None, "us": None}
-        ns = args.steps
-        host_out_t = {"J": torch.empty(ns * B, dtype=torch.float64).pin_memory(), "grad": torch.empty(ns * B, dtype=torch.float64).pin_memory(),
-                      "defect": torch.empty(ns * B, dtype=torch.float64).pin_memory(),
-                      "iters": torch.empty(ns * B, dtype=torch.int32).pin_memory(), "status": torch.empty(ns * B, dtype=torch.int32).pin_memory(),
-                      "xs": torch.empty(ns * B, wl.N + 1, solver.NS, dtype=torch.float64).pin_memory() if want_traj else None,
-                      "us": torch.empty(ns * B, wl.N, solver.NU, dtype=torch.float64).pin_memory() if want_traj else None}
-        host_out = {k: (None if v is None else v.numpy()) for k, v in host_out_t.items()}
-    gathered = [torch.empty(B, 5, dtype=torch.float64, device=dev) for _ in range(world)] if world > 1 else None
-
-    def gather(out):
-        if world > 1:   # the one collective of the path: per-problem summaries to every rank
-            summ = torch.stack((out["J"], out["grad"], out["defect"], out["iters"].double(), out["status"].double()), dim=1)
-            dist.all_gather(gathered, summ)
-
-    def run_steps(n, host):
-        """n steps, `depth` batches in flight; steps complete (and are gathered) in submission order."""
-        if stream_mode:
-            if host:
-                n = min(n, args.steps)
-                o = solver.solve_stream_host(x0_all_pin.numpy()[: n * B], trajectories=want_traj,
-                                             out={k: (None if v is None else v[: n * B]) for k, v in host_out.items()})
-                return {k: (None if v is None else v[(n - 1) * B: n * B]) for k, v in o.items()}
-            o = solver.solve_stream(x0_all_dev[: n * B], trajectories=False,
-                                    out={k: (None if v is None else v[: n * B]) for k, v in dev_out.items()})
-            torch.cuda.current_stream(dev).synchronize()
-            last = None
-            for k in range(n):
-                last = {key: (None if v is None else v[k * B:(k + 1) * B]) for key, v in o.items()}
-                gather(last)
-            return last
-        futs = []
-        for k in range(n):
-            if host:
-                futs.append(pipe.submit(x0_pin.numpy(), trajectories=want_traj, host=True, out=outs[k % depth][1]))
-            else:
-                futs.append(pipe.submit(x0_dev, trajectories=False))
-        last = None
-        for f in futs:
-            last = f.result()
-            if not host:
-                gather(last)
-        return last
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
+    leg = Leg(torch, dist, wl, B, rank * B, depth, dev, world, want_traj, args.compact)
+    solver = leg.solver
 
     if args.warmup > 0:
-        out = run_steps(args.warmup, False)
-    barrier()
+        leg.run_steps(args.warmup, False)
+    leg.barrier()
 
-    sampler = ClockSampler(torch.cuda.current_device() if os.environ.get("CUDA_VISIBLE_DEVICES") is None else local) if rank == 0 else None
+    smi_index = torch.cuda.current_device() if os.environ.get("CUDA_VISIBLE_DEVICES") is None else local
+    sampler = ClockSampler(smi_index) if rank == 0 else None
     launch_count(reset=True)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_lo = time.perf_counter()
-    barrier()
-    e0.record()
-    out = run_steps(args.steps, False)      # every lane synchronises its stream before its result is handed back
-    e1.record()
-    barrier()
+    ms_total, out = leg.timed_device(args.steps)
     t_hi = time.perf_counter()
     launches = launch_count(reset=True)
-    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms.item())
     clocks = sampler.stop(t_lo, t_hi) if sampler else None
 
     iters = out["iters"].cpu().numpy()
@@ -337,43 +475,72 @@ def run_gpu_arm(args):
     Jfin = out["J"].cpu().numpy()
 
     # ---- end to end through the host-buffer C-ABI call --------------------------------------
-    if args.e2e_inflight > 0 and not stream_mode:
-        pipe.active_depth = min(args.e2e_inflight, depth)
-    run_steps(min(depth, 2), True)
-    barrier()
-    t0 = time.perf_counter()
-    run_steps(args.steps, True)
-    barrier()
-    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    h2d = x0_rows.nbytes
-    if stream_mode:
-        out_np = {k: (None if v is None else v[(args.steps - 1) * B: args.steps * B]) for k, v in host_out.items()}
-    else:
-        out_np = outs[(args.steps - 1) % depth][1]
+    e2e_s, out_np = leg.timed_host(args.steps, args.e2e_inflight)
+    h2d = leg.x0_rows.nbytes
     d2h = sum(v.nbytes for v in out_np.values() if v is not None)
     assert np.array_equal(out_np["iters"], iters), "host-buffer path and device path disagree"
+    host_gbs, host_gbs_all = measure_host_d2h(torch, dist, dev, world)
 
-    pipe.active_depth = depth
     # ---- one batch alone (no overlap): latency of a step, and the serial throughput for comparison ----
-    barrier()
-    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s0.record()
-    out1 = solver.solve(x0_dev, trajectories=False)
-    s1.record()
-    torch.cuda.synchronize(dev)
-    serial_ms = s0.elapsed_time(s1)
+    serial_ms, out1 = leg.timed_single()
     assert np.array_equal(out1["iters"].cpu().numpy(), iters) and np.array_equal(out1["J"].cpu().numpy(), Jfin), \
         "pipelined and serial solves disagree"
 
     # ---- per-phase device time of one profiled step (event pairs around every launch) -------
     solver.set_profiling(True)
     solver.phase_times(reset=True)
-    solver.solve(x0_dev, trajectories=False)
+    solver.solve(leg.x0_dev, trajectories=False)
     torch.cuda.synchronize(dev)
     phases = solver.phase_times(reset=True)
     solver.set_profiling(False)
+    hist0 = solver.export_hist()["J_hist"][0].cpu().numpy()[: int(iters[0])]
+
+    # ---- the metric as worded: ONE global batch split over the ranks (strong scaling) --------
+    strong = None
+    G = STRONG_GLOBAL_BATCH[args.config]
+    if world > 1 and G % world == 0 and G // world <= 2 * args.batch and not args.no_strong:
+        leg.close()
+        Bs = G // world
+        wl_s = workloads.CONFIGS[args.config](B=G)
+        sdepth = auto_inflight(Bs)
+        sleg = Leg(torch, dist, wl_s, Bs, rank * Bs, sdepth, dev, world, want_traj, args.compact)
+        sleg.run_steps(max(args.warmup, 1), False)
+        s_ms, s_out = sleg.timed_device(args.steps)
+        s_e2e, s_np = sleg.timed_host(args.steps)
+        s_single_ms, _ = sleg.timed_single()
+        assert np.array_equal(s_np["iters"], s_out["iters"].cpu().numpy())
+        strong = {"global_batch": G, "batch_per_gpu": Bs, "inflight": sdepth, "scaling": "strong",
+                  "value": G * args.steps / (s_ms * 1e-3), "unit": "solves/s", "ms_per_step": s_ms / args.steps,
+                  "e2e": {"value": G * args.steps / s_e2e, "unit": "solves/s", "h2d_bytes_per_step": int(sleg.x0_rows.nbytes),
+                          "d2h_bytes_per_step": int(sum(v.nbytes for v in s_np.values() if v is not None))},
+                  "one_sweep_alone": {"ms": s_single_ms, "solves_per_s": G / (s_single_ms * 1e-3),
+                                      "note": "ONE 16k-problem sweep split over the ranks, nothing else in flight: its latency is the "
+                                              "slowest rank's solve of global_batch / n_gpus problems"},
+                  "note": "K sweeps of global_batch problems, each split over the ranks in contiguous shards; `inflight` sweeps in "
+                          "flight per GPU like the weak-scaling figure"}
+        sleg.close()
+
+    # ---- single-solve latency (the second half of BASELINE.json's metric): config 1, B = 1 ---
+    latency = None
+    if world == 1 and args.config == 3 and not args.no_latency:
+        wl1 = workloads.CONFIGS[1](B=1)
+        s1, x1 = wl1.make_solver(B=1, device=dev)
+        x1d = torch.as_tensor(x1, device=dev)
+        s1.solve(x1d, trajectories=False)
+        torch.cuda.synchronize(dev)
+        ts = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            o1 = s1.solve_host(x1)
+            ts.append(time.perf_counter() - t0)
+        J1 = s1.export_hist()["J_hist"][0].cpu().numpy()[: int(o1["iters"][0])]
+        latency = {"workload": "main_SE3ddp_tracking_exact.py (BASELINE configs[0]: SE3 single shooting, N=955, 13-step line search), B=1",
+                   "ms": 1e3 * statistics.median(ts), "iters": int(o1["iters"][0]), "decision_window_iters": decision_window(J1),
+                   "ms_per_iteration": 1e3 * statistics.median(ts) / max(int(o1["iters"][0]), 1), "J": float(o1["J"][0]),
+                   "timed": "trajopt_solve_host, host buffers in and out, wall clock, median of 3",
+                   "note": "iterations beyond the decision window are the rounding-noise tail of the 13-step line search (cost changes "
+                           "< 1e-12 relative); the oracle stops the same problem after 48"}
+        s1.close()
 
     if rank != 0:
         if world > 1:
@@ -388,14 +555,21 @@ def run_gpu_arm(args):
     fwd_ms, fwd_n = phases["forward"]
     oth_ms, _ = phases["other"]
     phase_total = bwd_ms + lin_ms + fwd_ms + oth_ms
-    peak = fp64_peak_tflops(60.0, dev)
+    psampler = ClockSampler(smi_index)
+    tp0 = time.perf_counter()
+    peak = fp64_peak_tflops(400.0, dev)
+    tp1 = time.perf_counter()
+    peak_clocks = psampler.stop(tp0, tp1)
     flop_bwd = model["flop_bwd"] * wl.N * sweeps
     achieved = flop_bwd / (bwd_ms * 1e-3) / 1e12 if bwd_ms > 0 else 0.0
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
-        with open(tpath) as f:
-            traffic = json.load(f).get("k_backward_dram_bytes_per_launch")
+    counters = load_kernel_counters(wl.kind)
+    traffic = executed = None
+    if counters:
+        traffic = counters.get("dram_bytes_per_launch")
+        fpu = (2.0 * counters["dfma"] + counters["dmul"] + counters["dadd"]) / counters["units"]
+        executed = {"flop_executed_per_unit": fpu, "flop_model_per_unit": model["flop_bwd"],
+                    "executed_tflops": fpu * wl.N * sweeps / (bwd_ms * 1e-3) / 1e12 if bwd_ms > 0 else 0.0,
+                    "fp64_pipe_active_frac_ncu": counters.get("fp64_pipe_active_frac"), "source": counters.get("source")}
     peaks = {}
     ppath = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(ppath):
@@ -407,18 +581,28 @@ def run_gpu_arm(args):
     bytes_step = model["bytes_bwd"] * wl.N * sweeps + model["bytes_fwd"] * wl.N * rollouts
 
     value = B * world / step_s
-    e2e_value = B * world * args.steps / float(e2e_s.item())
+    e2e_value = B * world * args.steps / e2e_s
     line = {
         "metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * step_s, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": workload_config(args, wl),
+        "value_returns": "per-problem summaries (J, grad, defect, iters, status); trajectories stay in HBM — `e2e` exports and copies them",
         "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "returns": "xs, us, J, grad, defect, iters, status" if want_traj else "J, grad, defect, iters, status"},
+                "returns": "xs, us, J, grad, defect, iters, status" if want_traj else "J, grad, defect, iters, status",
+                "host_d2h_gbs": host_gbs_all, "host_d2h_gbs_this_rank": host_gbs,
+                "host_d2h_used_frac": (d2h * world * args.steps / e2e_s / 1e9) / host_gbs_all if host_gbs_all else None,
+                "host_d2h_note": "concurrent pinned cudaMemcpyAsync of 1 GiB per rank, all ranks at once, summed: the ceiling the e2e "
+                                 "leg's trajectory copies share"},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "fp64", "kernel": "k_backward3 (Riccati sweep, 2-warp CTA per 32 problems)" if wl.kind != "so3" else "k_backward (Riccati sweep)", "achieved": achieved, "peak": peak,
+        "roofline": {"bound": "fp64", "kernel": "k_backward3 (Riccati sweep, 2-warp CTA per 32 problems)" if wl.kind not in ("so3", "pendulum") else "k_backward (Riccati sweep)", "achieved": achieved, "peak": peak,
                      "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": traffic,
+                     "frac_note": "model fraction: SURVEY 8d's DENSE flop count per stage-iteration over the measured time; the kernel "
+                                  "skips the structural zeros of f_x / f_u, see executed_frac for the FLOPs it actually issues",
+                     "executed_frac": executed["executed_tflops"] / peak if executed and peak else None,
+                     "executed": executed,
                      "peak_source": "DFMA microbenchmark run live by this bench (no FP64 entry in MEASURED_PEAKS.json)",
+                     "peak_clocks": peak_clocks,
                      "flop_per_launch": flop_bwd / max(bwd_n, 1), "launch_ms": bwd_ms / max(bwd_n, 1), "launches": int(bwd_n),
                      "share_of_step": bwd_ms / phase_total if phase_total else None},
         "solve_roofline": {"fp64_frac": flop_step / step_s / 1e12 / peak if peak else None,
@@ -440,8 +624,21 @@ def run_gpu_arm(args):
         "phases_ms": {"linearize": lin_ms, "backward": bwd_ms, "forward": fwd_ms, "other": oth_ms,
                       "launches": {"linearize": int(lin_n), "backward": int(bwd_n), "forward": int(fwd_n)}},
         "solve_stats": {"iters_mean": float(iters.mean()), "iters_min": int(iters.min()), "iters_max": int(iters.max()),
-                        "converged_frac": float(np.mean(status == 0)), "J_problem0": float(Jfin[0])},
+                        "converged_frac": float(np.mean(status == 0)), "J_problem0": float(Jfin[0]),
+                        "decision_window_iters": decision_window(hist0), "iters_problem0": int(iters[0]),
+                        "decision_window_note": "iterations of problem 0 whose cost change is above rounding noise (>= 1e-12 relative): "
+                                                "the span over which iteration counts / accepted step sizes are asserted equal to the "
+                                                "reference's (tests/test_gpu_golden.py, test_gpu_configs.py: 33 whole solves of this batch, "
+                                                "16..27 iterations, all inside their windows)"},
     }
+    if strong is not None:
+        line["strong"] = strong
+    elif world == 1 and G == B:
+        line["strong"] = {"global_batch": B, "batch_per_gpu": B, "scaling": "strong", "value": value, "unit": "solves/s",
+                          "e2e": {"value": e2e_value, "unit": "solves/s"}, "one_sweep_alone": {"ms": serial_ms, "solves_per_s": B / (serial_ms * 1e-3)},
+                          "note": "at one GPU the strong- and weak-scaling workloads coincide"}
+    if latency is not None:
+        line["single_solve_latency"] = latency
     if world == 1 and not args.no_cpu:
         try:
             v, cores, desc = cpu_sample_subprocess(args.config, 3, float(iters.mean()) + 1.0)
@@ -468,6 +665,8 @@ def main():
     ap.add_argument("--batch", type=int, default=None, help="problems per GPU")
     ap.add_argument("--no-traj", action="store_true", help="e2e leg returns only the per-problem summaries")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling leg (N > 1)")
+    ap.add_argument("--no-latency", action="store_true", help="skip the single-solve latency leg (N = 1, config 3)")
     ap.add_argument("--inflight", type=int, default=0,
                     help="batches in flight per GPU (1 = strictly one after the other; 0 = auto: 3, or 8 for batches <= 2048)")
     ap.add_argument("--e2e-inflight", type=int, default=0,
@@ -481,7 +680,7 @@ def main():
     if args.batch is None:
         args.batch = {1: 1, 2: 1024, 3: 16384, 4: 2048, 5: 131072}[args.config]
     if args.inflight <= 0:
-        args.inflight = 3 if args.batch > 2048 else 8
+        args.inflight = auto_inflight(args.batch)
     if args.schedule == "stream" and args.config == 4:
         raise SystemExit("--schedule stream: the augmented-Lagrangian method is solved per batch (use pipelined)")
     if args.impl == "reference":

@@ -20,6 +20,7 @@
  *                                            traopt_controller.py:1899-1924, 2463-2491, 2015-2028, 3123-3136
  *   trajopt_iterate                       <- the `for iteration in range(n_iterations)` loop body
  *                                            traopt_controller.py:1926-2007 (SS), 2493-2633 (MS), 3231-3264 (AL outer)
+ *   trajopt_iterate_inner                 <- AL: the inner fit()'s loop body, one iteration at a time (:3236-3240)
  *   trajopt_export / trajopt_export_hist  <- fit() return values and what the on_iteration callbacks record
  *                                            traopt_controller.py:2013, 2639, 3266-3267; benchmark_SE3_tracking.py:22-42
  *   trajopt_solve / trajopt_solve_host    <- one whole fit() for every problem of the batch; the batch itself
@@ -141,6 +142,12 @@ int trajopt_set_horizons(trajopt_handle* h, const int32_t* d_N, void* stream);
 int trajopt_begin(trajopt_handle* h, const double* d_x0, const double* d_us_init, int us_mode, void* stream);
 /* run up to n_iters more iterations; *n_active_out (may be NULL) = problems still running afterwards */
 int trajopt_iterate(trajopt_handle* h, int n_iters, int* n_active_out, void* stream);
+/* Augmented-Lagrangian handles: up to n_iters iterations of the INNER solve of the current outer iteration (the
+ * `on_iteration_ilqr` granularity of AL_iLQR_Tracking_SE3_MS.fit, traopt_controller.py:3236-3240); starts the next
+ * outer iteration's inner solve if the previous one has been closed.  *n_active_out = problems whose inner solve is
+ * still running; once it is 0, trajopt_iterate(h, 1, ...) closes the outer iteration (constraint evaluation and
+ * multiplier / penalty update, :3242-3264).  On other handles identical to trajopt_iterate. */
+int trajopt_iterate_inner(trajopt_handle* h, int n_iters, int* n_active_out, void* stream);
 /* any output pointer may be NULL.  d_xs [B][N+1][NS], d_us [B][N][NU], per-problem arrays [B] */
 int trajopt_export(trajopt_handle* h, double* d_xs, double* d_us, double* d_J, int32_t* d_iters,
                    int32_t* d_status, double* d_grad, double* d_defect, void* stream);

@@ -73,7 +73,7 @@ def test_second_solve_on_one_handle_after_compaction_keeps_references_and_horizo
     g = problems.load_golden("se3_n120")
     B, N = 1056, 30
     rng = np.random.default_rng(5)
-    shift = rng.integers(0, 80, size=B)
+    shift = rng.integers(0, 12, size=B)
     q_rows_all = layout.pose_rows(False, g["prob_q_ref"])
     q_rows = np.stack([q_rows_all[s:s + N + 1] for s in shift])
     xi_rows = np.stack([g["prob_xi_ref"][s:s + N + 1] for s in shift])
@@ -86,7 +86,7 @@ def test_second_solve_on_one_handle_after_compaction_keeps_references_and_horizo
         s.set_reference_batch(q_rows, xi_rows)
         s.set_horizons(horizons)
         if X0 is None:
-            X0 = gc.perturbed_x0(x0, B, scale=0.05)
+            X0 = gc.perturbed_x0(x0, B, scale=0.02)
         first = _all_outputs(s, X0)
         second = _all_outputs(s, X0)              # same handle, nothing set again
         res.append((first, second))
@@ -97,7 +97,7 @@ def test_second_solve_on_one_handle_after_compaction_keeps_references_and_horizo
                 assert np.array_equal(first[k], third[k]), k
         s.close()
     ref = res[0][0]
-    assert len(np.unique(ref["iters"])) > 2
+    assert len(np.unique(ref["iters"])) > 2 and np.all(np.isfinite(ref["J"]))
     for first, second in res:
         for k in ref:
             assert np.array_equal(ref[k], first[k]), k

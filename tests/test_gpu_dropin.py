@@ -192,3 +192,46 @@ def test_al_controller_with_velocity_bounds():
     assert seen[-1][0] and len(seen) == 6                       # oracle: 6 outer iterations
     assert seen[0][1:4] == ((N + 1, 24), (N + 1, 24, 24), (N + 1, 24))
     assert max(abs(x[1][2]) for x in xs) < 0.5 + 1e-2          # omega_z respects its bound
+
+
+def test_al_inner_callback_is_called_per_inner_iteration():
+    """`on_iteration_ilqr` (main_SE3ddp_tracking_exact_al_ms.py:14-16, traopt_controller.py:3236-3240): the inner fit of
+    every outer iteration calls it once per accepted iteration with the multiple-shooting callback's arguments, and the
+    returned histories are those of the LAST inner fit.  Stepping the device one inner iteration at a time changes no
+    number."""
+    from trajectory_optimization_matrix_lie_groups_b200 import workloads
+    from trajectory_optimization_matrix_lie_groups_b200.traoptlibrary import (traopt_constraints, traopt_controller as tc,
+                                                                              traopt_cost, traopt_dynamics)
+    N, dt = 40, 0.01
+    q_ref, xi_ref = workloads.helix_reference(N, dt)
+    Q = np.diag([10.0, 10, 10, 1, 1, 1, 1, 1, 1, 1, 1, 1])
+    dyn = traopt_dynamics.SE3Dynamics(np.diag([0.5, 0.7, 0.9, 1.0, 1.0, 1.0]), dt)
+    cost = traopt_cost.SE3TrackingQuadraticGaussNewtonCost(Q, np.zeros((6, 6)), 10 * Q, q_ref, xi_ref)
+    con = traopt_constraints.InputConstraint(-8.0, 8.0)
+    T0 = np.eye(4)
+    T0[:3, 3] = [-0.3, -0.3, -0.1]
+    x0 = [T0, np.array([0, 0, 0.1, 2.0, 0, 0.2])]
+    calls, outer = [], []
+
+    def cb_inner(iteration, xs, us, J_opt, accepted, converged, defect_norm, grad_norm, alpha, mu, J_hist, xs_hist, us_hist,
+                 grad_hist, defect_hist):
+        calls.append((len(outer), iteration, J_opt, accepted))
+        _cb_ms(iteration, xs, us, J_opt, accepted, converged, defect_norm, grad_norm, alpha, mu, J_hist, xs_hist, us_hist,
+               grad_hist, defect_hist)
+
+    def cb_outer(iteration, constr_converged, lmbd, Imu, mu, constr_eval, lmbd_hist, mu_hist, violation_hist, nactive_hist):
+        outer.append((iteration, constr_converged, float(np.max(constr_eval))))
+        violation_hist.append(float(np.max(constr_eval)))
+
+    ctrl = tc.AL_iLQR_Tracking_SE3_MS(dyn, cost, con, N, q_ref, xi_ref)
+    a = ctrl.fit(x0, np.zeros((N, 6)), n_al_iters=15, n_ilqr_iters=60, on_iteration_al=cb_outer, on_iteration_ilqr=cb_inner)
+    ctrl2 = tc.AL_iLQR_Tracking_SE3_MS(dyn, cost, con, N, q_ref, xi_ref)
+    b = ctrl2.fit(x0, np.zeros((N, 6)), n_al_iters=15, n_ilqr_iters=60)
+    assert np.array_equal(a[1], b[1]) and len(outer) == 10 and outer[-1][1]
+    per_outer = np.bincount([c[0] for c in calls], minlength=len(outer))
+    assert np.all(per_outer >= 1)
+    assert all(c[3] for c in calls)
+    # histories of the last inner fit, filled by the callback; they equal the device's own (returned when no callback is given)
+    assert len(a[2]) == per_outer[-1] == len(b[2]) and np.allclose(a[2], b[2], rtol=0, atol=0)
+    assert len(a[3]) == per_outer[-1] + 1 and len(a[4]) == per_outer[-1] + 1      # initial guess + one entry per iteration
+    assert [c[1] for c in calls if c[0] == len(outer) - 1] == list(range(per_outer[-1]))

@@ -76,6 +76,7 @@ SYMBOLS = {
     "trajopt_solve_stream_host": (_I, [_P, _P, C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "trajopt_begin": (_I, [_P, _P, _P, _I, _P]),
     "trajopt_iterate": (_I, [_P, _I, C.POINTER(_I), _P]),
+    "trajopt_iterate_inner": (_I, [_P, _I, C.POINTER(_I), _P]),
     "trajopt_export": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "trajopt_export_hist": (_I, [_P, _P, _P, _P, _P, _P]),
     "trajopt_export_al": (_I, [_P, _P, _P, _P, _P, _P, _P]),

@@ -321,6 +321,14 @@ int trajopt_iterate(trajopt_handle* h, int n_iters, int* n_active_out, void* str
     return DISPATCH_KIND(h, iterate_impl, h, n_iters, n_active_out, (cudaStream_t)stream);
 }
 
+int trajopt_iterate_inner(trajopt_handle* h, int n_iters, int* n_active_out, void* stream) {
+    if (!h) return fail(TRAJOPT_E_INVALID, "trajopt_iterate_inner: NULL handle");
+    if (!h->begun) return fail(TRAJOPT_E_STATE, "trajopt_iterate_inner: call trajopt_begin first");
+    if (n_iters < 0) return fail(TRAJOPT_E_INVALID, "trajopt_iterate_inner: n_iters < 0");
+    DeviceGuard guard(h->device);
+    return DISPATCH_KIND(h, iterate_inner_impl, h, n_iters, n_active_out, (cudaStream_t)stream);
+}
+
 int trajopt_export(trajopt_handle* h, double* d_xs, double* d_us, double* d_J, int32_t* d_iters, int32_t* d_status,
                    double* d_grad, double* d_defect, void* stream) {
     if (!h) return fail(TRAJOPT_E_INVALID, "trajopt_export: NULL handle");
@@ -329,8 +337,8 @@ int trajopt_export(trajopt_handle* h, double* d_xs, double* d_us, double* d_J, i
     cudaStream_t s = (cudaStream_t)stream;
     const Work& w = h->w;
     const int bg = blocks_for(h->Bp, 128);
-    if (d_xs) LAUNCH(k_export_traj, export_grid(h, (h->N + 1) * (h->NS)), 128, 0, s, h->B, h->Bp, h->NS, w.X[0], w.X[1], w.sel, (const int*)h->w.orig, d_xs, h->N + 1);
-    if (d_us) LAUNCH(k_export_traj, export_grid(h, (h->N) * (h->NU)), 128, 0, s, h->B, h->Bp, h->NU, w.U[0], w.U[1], w.sel, (const int*)h->w.orig, d_us, h->N);
+    if (d_xs) LAUNCH(k_export_traj, export_grid(h, (h->N + 1) * (h->NS)), 128, 0, s, h->B, h->Bp, h->NS, w.X[0], w.X[1], w.sel, (const int*)h->w.orig, d_xs, h->N + 1, h->var_horizons ? (const int*)w.Nb : (const int*)nullptr, 0);
+    if (d_us) LAUNCH(k_export_traj, export_grid(h, (h->N) * (h->NU)), 128, 0, s, h->B, h->Bp, h->NU, w.U[0], w.U[1], w.sel, (const int*)h->w.orig, d_us, h->N, h->var_horizons ? (const int*)w.Nb : (const int*)nullptr, 1);
     if (d_J) LAUNCH(k_export_rows<double>, dim3(bg, 1), 128, 0, s, h->B, h->Bp, 1, w.J, (const int*)h->w.orig, d_J);
     if (d_grad) LAUNCH(k_export_rows<double>, dim3(bg, 1), 128, 0, s, h->B, h->Bp, 1, w.grad, (const int*)h->w.orig, d_grad);
     if (d_defect) LAUNCH(k_export_rows<double>, dim3(bg, 1), 128, 0, s, h->B, h->Bp, 1, w.dnorm, (const int*)h->w.orig, d_defect);
@@ -375,8 +383,8 @@ int trajopt_export_al(trajopt_handle* h, double* d_lmbd, double* d_imu, double* 
     cudaStream_t s = (cudaStream_t)stream;
     const Work& w = h->w;
     const int bg = blocks_for(h->Bp, 128);
-    if (d_lmbd) LAUNCH(k_export_traj, export_grid(h, (h->N + 1) * (2 * h->NU)), 128, 0, s, h->B, h->Bp, 2 * h->NU, w.lam, w.lam, (const int*)nullptr, (const int*)h->w.orig, d_lmbd, h->N + 1);
-    if (d_imu) LAUNCH(k_export_traj, export_grid(h, (h->N + 1) * (2 * h->NU)), 128, 0, s, h->B, h->Bp, 2 * h->NU, w.imu, w.imu, (const int*)nullptr, (const int*)h->w.orig, d_imu, h->N + 1);
+    if (d_lmbd) LAUNCH(k_export_traj, export_grid(h, (h->N + 1) * (2 * h->NU)), 128, 0, s, h->B, h->Bp, 2 * h->NU, w.lam, w.lam, (const int*)nullptr, (const int*)h->w.orig, d_lmbd, h->N + 1, (const int*)nullptr, 0);
+    if (d_imu) LAUNCH(k_export_traj, export_grid(h, (h->N + 1) * (2 * h->NU)), 128, 0, s, h->B, h->Bp, 2 * h->NU, w.imu, w.imu, (const int*)nullptr, (const int*)h->w.orig, d_imu, h->N + 1, (const int*)nullptr, 0);
     if (d_mu) LAUNCH(k_export_rows<double>, dim3(bg, 1), 128, 0, s, h->B, h->Bp, 1, w.al_mu, (const int*)h->w.orig, d_mu);
     if (d_violation) LAUNCH(k_export_rows<double>, dim3(bg, 1), 128, 0, s, h->B, h->Bp, 1, w.al_viol, (const int*)h->w.orig, d_violation);
     if (d_outer_iters) LAUNCH(k_export_rows<int>, dim3(bg, 1), 128, 0, s, h->B, h->Bp, 1, w.al_outer, (const int*)h->w.orig, (int*)d_outer_iters);
@@ -391,8 +399,8 @@ int trajopt_export_al_state(trajopt_handle* h, double* d_lmbd_state, double* d_i
     cudaStream_t s = (cudaStream_t)stream;
     const Work& w = h->w;
     const int bg = blocks_for(h->Bp, 128), cw = 2 * (h->NX - h->NP);
-    if (d_lmbd_state) LAUNCH(k_export_traj, export_grid(h, (h->N + 1) * (cw)), 128, 0, s, h->B, h->Bp, cw, w.lam_s, w.lam_s, (const int*)nullptr, (const int*)h->w.orig, d_lmbd_state, h->N + 1);
-    if (d_imu_state) LAUNCH(k_export_traj, export_grid(h, (h->N + 1) * (cw)), 128, 0, s, h->B, h->Bp, cw, w.imu_s, w.imu_s, (const int*)nullptr, (const int*)h->w.orig, d_imu_state, h->N + 1);
+    if (d_lmbd_state) LAUNCH(k_export_traj, export_grid(h, (h->N + 1) * (cw)), 128, 0, s, h->B, h->Bp, cw, w.lam_s, w.lam_s, (const int*)nullptr, (const int*)h->w.orig, d_lmbd_state, h->N + 1, (const int*)nullptr, 0);
+    if (d_imu_state) LAUNCH(k_export_traj, export_grid(h, (h->N + 1) * (cw)), 128, 0, s, h->B, h->Bp, cw, w.imu_s, w.imu_s, (const int*)nullptr, (const int*)h->w.orig, d_imu_state, h->N + 1, (const int*)nullptr, 0);
     return 0;
 }
 
@@ -561,8 +569,8 @@ int trajopt_solve_host(trajopt_handle* h, const double* h_x0, const double* h_us
     if (early) {   // only the stragglers' rows are new; s_status still holds the snapshot of the early export
         const int bg = blocks_for(h->Bp, 128);
         const Work& w = h->w;
-        if (h_xs) LAUNCH(k_export_traj_late, export_grid(h, (h->N + 1) * (h->NS)), 128, 0, s, h->B, h->Bp, h->NS, w.X[0], w.X[1], w.sel, (const int*)w.orig, (const int*)h->s_status, h->s_xs, h->N + 1);
-        if (h_us) LAUNCH(k_export_traj_late, export_grid(h, (h->N) * (h->NU)), 128, 0, s, h->B, h->Bp, h->NU, w.U[0], w.U[1], w.sel, (const int*)w.orig, (const int*)h->s_status, h->s_us, h->N);
+        if (h_xs) LAUNCH(k_export_traj_late, export_grid(h, (h->N + 1) * (h->NS)), 128, 0, s, h->B, h->Bp, h->NS, w.X[0], w.X[1], w.sel, (const int*)w.orig, (const int*)h->s_status, h->s_xs, h->N + 1, h->var_horizons ? (const int*)w.Nb : (const int*)nullptr, 0);
+        if (h_us) LAUNCH(k_export_traj_late, export_grid(h, (h->N) * (h->NU)), 128, 0, s, h->B, h->Bp, h->NU, w.U[0], w.U[1], w.sel, (const int*)w.orig, (const int*)h->s_status, h->s_us, h->N, h->var_horizons ? (const int*)w.Nb : (const int*)nullptr, 1);
     }
     if ((rc = trajopt_export(h, (!early && h_xs) ? h->s_xs : nullptr, (!early && h_us) ? h->s_us : nullptr, h->s_J, h->s_iters,
                              h->s_status, h->s_grad, h->s_def, stream)))
@@ -619,8 +627,8 @@ int trajopt_debug_gains(trajopt_handle* h, double* d_k, double* d_K, void* strea
     DeviceGuard guard(h->device);
     cudaStream_t s = (cudaStream_t)stream;
     const int bg = blocks_for(h->Bp, 128);
-    if (d_k) LAUNCH(k_export_traj, export_grid(h, (h->N) * (h->NU)), 128, 0, s, h->B, h->Bp, h->NU, h->w.kff, h->w.kff, (const int*)nullptr, (const int*)h->w.orig, d_k, h->N);
-    if (d_K) LAUNCH(k_export_traj, export_grid(h, (h->N) * (h->NU * h->NX)), 128, 0, s, h->B, h->Bp, h->NU * h->NX, h->w.Kfb, h->w.Kfb, (const int*)nullptr, (const int*)h->w.orig, d_K, h->N);
+    if (d_k) LAUNCH(k_export_traj, export_grid(h, (h->N) * (h->NU)), 128, 0, s, h->B, h->Bp, h->NU, h->w.kff, h->w.kff, (const int*)nullptr, (const int*)h->w.orig, d_k, h->N, (const int*)nullptr, 0);
+    if (d_K) LAUNCH(k_export_traj, export_grid(h, (h->N) * (h->NU * h->NX)), 128, 0, s, h->B, h->Bp, h->NU * h->NX, h->w.Kfb, h->w.Kfb, (const int*)nullptr, (const int*)h->w.orig, d_K, h->N, (const int*)nullptr, 0);
     return 0;
 }
 

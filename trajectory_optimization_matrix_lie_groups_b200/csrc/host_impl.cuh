@@ -56,6 +56,7 @@ struct trajopt_handle {
     bool inner_done = true;  // the inner loop of the current fit() / AL outer iteration has ended
     int al_outer = 0;        // AL outer iterations completed
     bool al_finished = false;
+    bool al_inner_open = false;   // AL: an inner solve has been started and its multiplier update has not been applied yet
     int hist_cap = -1, cand_rows = -1;
     // compaction: leading slots that may hold running problems; thresholds (see maybe_compact)
     int front = 0, compact_min_batch = 1024, compact_ratio = 4;
@@ -520,6 +521,7 @@ int begin_impl(trajopt_handle* h, const double* d_x0, const double* d_us_init, i
     h->al_finished = false;
     int rc = start_inner<KIND>(h, s, false);
     if (rc) return rc;
+    h->al_inner_open = true;
     h->begun = true;
     return 0;
 }
@@ -537,10 +539,12 @@ int iterate_impl(trajopt_handle* h, int n_iters, int* n_active_out, cudaStream_t
     // augmented Lagrangian: one unit = one outer iteration (:3231-3264)
     int remaining = 1;
     for (int j = 0; j < n_iters && !h->al_finished; ++j) {
-        if (h->inner_done) {
+        if (!h->al_inner_open) {
             if ((rc = start_inner<KIND>(h, s, true))) return rc;   // cold restart (:3237)
+            h->al_inner_open = true;
         }
-        if ((rc = run_inner<KIND>(h, s, h->prm.max_iters + 1, &act))) return rc;
+        if (!h->inner_done && (rc = run_inner<KIND>(h, s, h->prm.max_iters + 1, &act))) return rc;
+        h->al_inner_open = false;
         {
             PhaseTimer t(h, s, PH_OTHER);
             CUDA_OK(cudaMemsetAsync(h->w.counters, 0, 4 * sizeof(int), s));
@@ -554,6 +558,27 @@ int iterate_impl(trajopt_handle* h, int n_iters, int* n_active_out, cudaStream_t
         if (remaining == 0 || h->al_outer >= h->user.n_al_iters) h->al_finished = true;
     }
     if (n_active_out) *n_active_out = h->al_finished ? 0 : remaining;
+    return 0;
+}
+
+// Augmented Lagrangian, inner iterations one at a time (trajopt_iterate_inner): up to n_iters iterations of the inner
+// solve of the CURRENT outer iteration (started here if the previous one has been closed by trajopt_iterate).  The
+// multiplier update stays with trajopt_iterate.  *n_active_out = problems whose inner solve is still running.
+template <int KIND>
+int iterate_inner_impl(trajopt_handle* h, int n_iters, int* n_active_out, cudaStream_t s) {
+    if (h->method != TRAJOPT_AL_MS) return iterate_impl<KIND>(h, n_iters, n_active_out, s);
+    int rc, act = 0;
+    if (!h->al_finished) {
+        if (!h->al_inner_open) {
+            if ((rc = start_inner<KIND>(h, s, true))) return rc;
+            h->al_inner_open = true;
+        }
+        if (h->inner_done) {
+            if ((rc = count_running(h, s, &act))) return rc;
+        } else if ((rc = run_inner<KIND>(h, s, n_iters, &act))) return rc;
+        if (h->inner_done) act = 0;
+    }
+    if (n_active_out) *n_active_out = act;
     return 0;
 }
 
@@ -620,6 +645,7 @@ inline int ensure_hist(trajopt_handle* h) {
     template int trajopt_host::set_reference_batch_impl<K>(trajopt_handle*, const double*, const double*, cudaStream_t);        \
     template int trajopt_host::begin_impl<K>(trajopt_handle*, const double*, const double*, int, cudaStream_t);                  \
     template int trajopt_host::iterate_impl<K>(trajopt_handle*, int, int*, cudaStream_t);                                        \
+    template int trajopt_host::iterate_inner_impl<K>(trajopt_handle*, int, int*, cudaStream_t);                                  \
     template int trajopt_host::solve_stream_impl<K>(trajopt_handle*, const double*, int, double*, double*, double*, int*, int*, \
                                                     double*, double*, cudaStream_t);                                             \
     template int trajopt_host::debug_linearize_impl<K>(trajopt_handle*, double*, double*, double*, double*, double*, double*,   \
@@ -630,6 +656,7 @@ inline int ensure_hist(trajopt_handle* h) {
     extern template int trajopt_host::set_reference_batch_impl<K>(trajopt_handle*, const double*, const double*, cudaStream_t); \
     extern template int trajopt_host::begin_impl<K>(trajopt_handle*, const double*, const double*, int, cudaStream_t);           \
     extern template int trajopt_host::iterate_impl<K>(trajopt_handle*, int, int*, cudaStream_t);                                 \
+    extern template int trajopt_host::iterate_inner_impl<K>(trajopt_handle*, int, int*, cudaStream_t);                           \
     extern template int trajopt_host::solve_stream_impl<K>(trajopt_handle*, const double*, int, double*, double*, double*,      \
                                                            int*, int*, double*, double*, cudaStream_t);                          \
     extern template int trajopt_host::debug_linearize_impl<K>(trajopt_handle*, double*, double*, double*, double*, double*,     \

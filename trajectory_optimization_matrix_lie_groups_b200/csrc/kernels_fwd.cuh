@@ -682,8 +682,10 @@ __global__ void k_al_init(const Params prm, Work w, double mu0) {
 // slots = one 32-byte sector) share through L1.  (One thread per (slot, stage) writing F doubles took 4-9 ms for the
 // 2.4 GB of a headline batch.)  grid = (ceil(Bp / 4), chunks of kExportChunk elements), block = 128.
 constexpr int kExportChunk = 2048;
+// Nb (NULL: every problem uses all nstage rows): rows of stages > Nb[b] - nb_shift were never written by a rollout; they
+// are taken from buffer 0, which holds the initial guess there (nb_shift = 0 for states, 1 for controls).
 static __global__ void k_export_traj(int B, int Bp, int F, const double* s0, const double* s1, const int* sel,
-                                     const int* __restrict__ orig, double* out, int nstage) {
+                                     const int* __restrict__ orig, double* out, int nstage, const int* __restrict__ Nb, int nb_shift) {
     const int b = blockIdx.x * 4 + (threadIdx.x >> 5);      // slot
     if (b >= Bp) return;
     const int o = orig[b];                                  // the caller's problem index
@@ -691,12 +693,14 @@ static __global__ void k_export_traj(int B, int Bp, int F, const double* s0, con
     const double* src = ((sel && sel[b]) ? s1 : s0) + b;
     const int len = nstage * F, lane = threadIdx.x & 31;
     const int e0 = blockIdx.y * kExportChunk, e1 = min(e0 + kExportChunk, len);
+    const int e_own = Nb ? min(len, (Nb[b] - nb_shift + 1) * F) : len;      // elements [0, e_own) belong to the solved horizon
     double* dst = out + (size_t)o * len;
-    for (int e = e0 + lane; e < e1; e += 32) dst[e] = src[(size_t)e * Bp];
+    for (int e = e0 + lane; e < e1; e += 32) dst[e] = (e < e_own ? src : s0 + b)[(size_t)e * Bp];
 }
 // the same for the problems that were still running when `snap` (status by caller index) was taken
 static __global__ void k_export_traj_late(int B, int Bp, int F, const double* s0, const double* s1, const int* sel,
-                                          const int* __restrict__ orig, const int* __restrict__ snap, double* out, int nstage) {
+                                          const int* __restrict__ orig, const int* __restrict__ snap, double* out, int nstage,
+                                          const int* __restrict__ Nb, int nb_shift) {
     const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (b >= Bp) return;
     const int o = orig[b];
@@ -704,8 +708,9 @@ static __global__ void k_export_traj_late(int B, int Bp, int F, const double* s0
     const double* src = ((sel && sel[b]) ? s1 : s0) + b;
     const int len = nstage * F, lane = threadIdx.x & 31;
     const int e0 = blockIdx.y * kExportChunk, e1 = min(e0 + kExportChunk, len);
+    const int e_own = Nb ? min(len, (Nb[b] - nb_shift + 1) * F) : len;
     double* dst = out + (size_t)o * len;
-    for (int e = e0 + lane; e < e1; e += 32) dst[e] = src[(size_t)e * Bp];
+    for (int e = e0 + lane; e < e1; e += 32) dst[e] = (e < e_own ? src : s0 + b)[(size_t)e * Bp];
 }
 // out[orig[b]][row] = src[row][b]
 template <typename T>

@@ -164,6 +164,12 @@ class BatchSolver:
         check(lib.trajopt_iterate(self._h, int(n_iters), C.byref(act), _stream(self.device)))
         return act.value
 
+    def iterate_inner(self, n_iters=1):
+        """AL handles: inner iterations of the current outer iteration; returns the problems whose inner solve still runs."""
+        act = C.c_int(0)
+        check(lib.trajopt_iterate_inner(self._h, int(n_iters), C.byref(act), _stream(self.device)))
+        return act.value
+
     def _new(self, *shape, dtype=torch.float64):
         return torch.empty(*shape, dtype=dtype, device=self.device)
 

@@ -150,6 +150,40 @@ class _NativeController(BaseController):
         k, K = s.debug_gains()
         self._k, self._K = k[0].cpu().numpy(), K[0].cpu().numpy()
 
+    def _ms_callback_loop(self, s, step, n_iterations, on_iteration, J_hist, xs_hist, us_hist, grad_hist, defect_hist):
+        """The `for iteration in range(n_iterations)` loop of the multiple-shooting `fit` (traopt_controller.py:2493-2633)
+        with the scripts' callback protocol; `step()` advances the device by one iteration.  Returns (out, hist, status).
+
+        Iteration j's cost and new defect are evaluated by the device in pass j+1 (they are the stage costs / defects
+        of the next linearisation), so its callback fires one pass later."""
+        kind = self._kind
+        alphas = self._alphas()
+        pending = None
+        out = h = None
+        status = _lib.STATUS_RUNNING
+        for j in range(n_iterations + 1):
+            step()
+            out = s.export()
+            h = s.export_hist()
+            status = int(out["status"][0]) & 15
+            if j == 0:
+                defect_hist.append(float(h["defect_hist"][0, 0]))              # appended by fit at iteration 0 (:2505-2506)
+            if pending is not None:
+                pj, pxs, pus, pmu, pa = pending
+                accepted = pa >= 0
+                on_iteration(pj, pxs, pus, float(h["J_hist"][0, pj]), accepted, False, float(h["defect_hist"][0, pj + 1]),
+                             np.float64(h["grad_hist"][0, pj].item()), float(alphas[pa]) if self._line_search and accepted else 1,
+                             pmu, J_hist, xs_hist, us_hist, grad_hist, defect_hist)
+                pending = None
+                if not accepted:
+                    break
+            if status != _lib.STATUS_RUNNING:
+                break
+            self._mu = float(s.export_reg()[0][0])
+            pending = (j, _native.rows_states(kind, out["xs"][0].cpu().numpy()), out["us"][0].cpu().numpy(), self._mu,
+                       int(h["alpha_hist"][0, j]))
+        return out, h, status
+
     # -------------------------------------------------------------------------------- fit_batch
     def fit_batch(self, x0_batch, us_init=None, n_iterations=100, tol_grad_norm=None, tol_d_norm=1e-6,
                   return_trajectories=True, return_hist=False, device=None, shard=None, q_ref_batch=None,
@@ -320,30 +354,8 @@ class _MultipleShooting(_NativeController):
             status = int(out["status"][0]) & 15
             defect_hist.append(float(h["defect_hist"][0, 0]))              # appended by fit at iteration 0 (:2505-2506)
         else:
-            # Iteration j's cost and new defect are evaluated by the device in pass j+1 (they are the
-            # stage costs / defects of the next linearisation), so its callback fires one pass later.
-            pending = None
-            for j in range(n_iterations + 1):
-                s.iterate(1)
-                out = s.export()
-                h = s.export_hist()
-                status = int(out["status"][0]) & 15
-                if j == 0:
-                    defect_hist.append(float(h["defect_hist"][0, 0]))
-                if pending is not None:
-                    pj, pxs, pus, pmu, pa = pending
-                    accepted = pa >= 0
-                    on_iteration(pj, pxs, pus, float(h["J_hist"][0, pj]), accepted, False, float(h["defect_hist"][0, pj + 1]),
-                                 np.float64(h["grad_hist"][0, pj].item()), float(alphas[pa]) if self._line_search and accepted else 1,
-                                 pmu, J_hist, xs_hist, us_hist, grad_hist, defect_hist)
-                    pending = None
-                    if not accepted:
-                        break
-                if status != _lib.STATUS_RUNNING:
-                    break
-                self._mu = float(s.export_reg()[0][0])
-                pending = (j, _native.rows_states(kind, out["xs"][0].cpu().numpy()), out["us"][0].cpu().numpy(), self._mu,
-                           int(h["alpha_hist"][0, j]))
+            out, h, status = self._ms_callback_loop(s, lambda: s.iterate(1), n_iterations, on_iteration, J_hist, xs_hist,
+                                                    us_hist, grad_hist, defect_hist)
         if status == _lib.STATUS_CONVERGED and self.APPEND_FINAL_GRAD:
             grad_hist.append(float(out["grad"][0]))
         if status == _lib.STATUS_NO_DESCENT:
@@ -404,19 +416,28 @@ class AL_iLQR_Tracking_SE3_MS(_NativeController):
     def fit(self, x0, us_init, n_al_iters=100, n_ilqr_iters=200, tol_J=1e-6, tol_grad_norm=1e-6, tol_constr=1e-2,
             on_iteration_al=None, on_iteration_ilqr=None):
         """Returns (xs, us, J_hist, xs_hist, us_hist, grad_hist, lmbd_hist, mu_hist, violation_hist, nactive_hist)."""
-        if on_iteration_ilqr is not None:
-            warnings.warn("on_iteration_ilqr is not called: the inner solves of an outer iteration run on the device in one piece")
         kind = self._kind
         s = self._solver(1, None, **self._al_params(n_al_iters, n_ilqr_iters, tol_constr))
         s.begin(_native.state_row(kind, x0)[None, :], np.array(us_init, dtype=float))
         lmbd_hist, mu_hist, violation_hist, nactive_hist = [], [], [], []
+        J_hist, xs_hist, us_hist, grad_hist, defect_hist = [], [], [], [], []
         c = self._constr_size
         for it in range(n_al_iters):
             al = s.export_al()                              # multipliers this outer iteration is solved with
             lmbd = al["lmbd"][0].cpu().numpy()
             Imu = np.stack([np.diag(r) for r in al["imu"][0].cpu().numpy()])
             mu = float(al["mu"][0])
-            active = s.iterate(1)
+            if on_iteration_ilqr is not None:
+                # the inner fit() of this outer iteration, one device iteration per callback (:3236-3240); its history
+                # lists start afresh like those of every iLQR_Tracking_SE3_MS.fit call (:2478-2491)
+                J_hist, xs_hist, us_hist, grad_hist, defect_hist = [], [], [], [], []
+                s.iterate_inner(0)                          # opens the inner solve (cold start) without iterating
+                o0 = s.export()
+                xs_hist.append(_native.rows_states(kind, o0["xs"][0].cpu().numpy()))
+                us_hist.append(o0["us"][0].cpu().numpy())
+                self._ms_callback_loop(s, lambda: s.iterate_inner(1), n_ilqr_iters, on_iteration_ilqr, J_hist, xs_hist,
+                                       us_hist, grad_hist, defect_hist)
+            active = s.iterate(1)                           # (rest of) the inner solve + constraint evaluation + update
             out = s.export()
             us = out["us"][0].cpu().numpy()
             if hasattr(self.constr, "xi_lb"):
@@ -441,8 +462,9 @@ class AL_iLQR_Tracking_SE3_MS(_NativeController):
         xs = _native.rows_states(kind, out["xs"][0].cpu().numpy())
         us = out["us"][0].cpu().numpy()
         self.last_result = {k: v.cpu().numpy() for k, v in {**out, **h, **s.export_al()}.items()}
-        return (xs, us, h["J_hist"][0, :n].cpu().numpy().tolist(), [], [], h["grad_hist"][0, :n].cpu().numpy().tolist(),
-                lmbd_hist, mu_hist, violation_hist, nactive_hist)
+        if on_iteration_ilqr is None:      # no callback to fill the lists: the device's own histories of the last inner solve
+            J_hist, grad_hist = h["J_hist"][0, :n].cpu().numpy().tolist(), h["grad_hist"][0, :n].cpu().numpy().tolist()
+        return xs, us, J_hist, xs_hist, us_hist, grad_hist, lmbd_hist, mu_hist, violation_hist, nactive_hist
 
     def fit_batch(self, x0_batch, us_init=None, n_al_iters=100, n_ilqr_iters=200, tol_constr=1e-2, **kw):
         return super().fit_batch(x0_batch, us_init, n_iterations=n_ilqr_iters, tol_grad_norm=1e-6, tol_d_norm=1e-6,
