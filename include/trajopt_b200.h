@@ -214,6 +214,12 @@ int trajopt_set_profiling(trajopt_handle* h, int enable);
  * min_batch < 0 disables it. */
 int trajopt_set_compaction(trajopt_handle* h, int min_batch, int ratio);
 
+/* Backward sweep of the SE3 / quadrotor / rigid-body families (_backward_pass, traopt_controller.py:2178-2261 / 2912-3006):
+ * variant 0 = automatic (CTAs of four warps per 32 problems while the slots in use fit one wave of them on the device,
+ * counting `lanes` solver handles that share it; CTAs of two warps above), 2 / 4 = always that variant.  The variants are
+ * bit-identical; this only changes how a launch maps onto the SMs.  Defaults 0, 1. */
+int trajopt_set_sweep(trajopt_handle* h, int variant, int lanes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libtrajopt_b200.so")
+# TRAJOPT_LIB: an A/B build of the same library (see build.py), for kernel experiments only
+LIB_PATH = os.environ.get("TRAJOPT_LIB") or os.path.join(HERE, "libtrajopt_b200.so")
 
 SO3, SE3, DRONE, RIGID, PEND = 0, 1, 2, 3, 4
 SS, MS, AL_MS = 0, 1, 2
@@ -95,6 +96,7 @@ SYMBOLS = {
     "trajopt_phase_times": (_I, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64), _I]),
     "trajopt_set_profiling": (_I, [_P, _I]),
     "trajopt_set_compaction": (_I, [_P, _I, _I]),
+    "trajopt_set_sweep": (_I, [_P, _I, _I]),
 }
 
 

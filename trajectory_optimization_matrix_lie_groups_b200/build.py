@@ -20,6 +20,13 @@ SOURCES = ["api.cu", "kind_so3.cu", "kind_se3.cu", "kind_drone.cu", "kind_rigid.
 HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + [os.path.join("..", "..", "include", "trajopt_b200.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
+# A/B builds of kernel experiments: TRAJOPT_NVCC_EXTRA="-DFOO ..." adds flags, TRAJOPT_LIB_SUFFIX=_foo writes
+# libtrajopt_b200_foo.so (objects under build_foo/) next to the product library; `TRAJOPT_LIB=<path>` makes _lib.py load it.
+EXTRA = os.environ.get("TRAJOPT_NVCC_EXTRA", "").split()
+SUFFIX = os.environ.get("TRAJOPT_LIB_SUFFIX", "")
+if SUFFIX:
+    OBJ = os.path.join(HERE, "build" + SUFFIX)
+    LIB = os.path.join(HERE, f"libtrajopt_b200{SUFFIX}.so")
 
 
 def _stale():
@@ -32,7 +39,7 @@ def _stale():
 
 def _compile(nvcc, src, verbose):
     obj = os.path.join(OBJ, os.path.splitext(src)[0] + ".o")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+    cmd = [nvcc] + NVCC_FLAGS + EXTRA + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)

@@ -70,6 +70,7 @@ int trajopt_create(int kind, int method, int N, int B, int device, trajopt_handl
     trajopt_handle* h = new (std::nothrow) trajopt_handle();
     if (!h) return fail(TRAJOPT_E_INVALID, "trajopt_create: out of host memory");
     h->kind = kind; h->method = method; h->N = N; h->B = B; h->device = device;
+    if (cudaDeviceGetAttribute(&h->sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || h->sms < 1) h->sms = 148;
     h->Bp = (B + kBlock - 1) / kBlock * kBlock;
     if (kind == TRAJOPT_SO3) { h->NX = 6; h->NP = 3; h->NU = 3; h->NS = 7; h->LEN = LinRec<TRAJOPT_SO3>::LEN; h->REFROW = RefRow<TRAJOPT_SO3>::N; }
     else if (kind == TRAJOPT_PEND) { h->NX = 6; h->NP = 3; h->NU = 3; h->NS = 7; h->LEN = LinRec<TRAJOPT_PEND>::LEN; h->REFROW = RefRow<TRAJOPT_PEND>::N; }
@@ -721,6 +722,14 @@ int trajopt_set_compaction(trajopt_handle* h, int min_batch, int ratio) {
     if (ratio < 1) return fail(TRAJOPT_E_INVALID, "trajopt_set_compaction: ratio must be >= 1");
     h->compact_min_batch = min_batch;
     h->compact_ratio = ratio;
+    return 0;
+}
+
+int trajopt_set_sweep(trajopt_handle* h, int variant, int lanes) {
+    if (!h) return fail(TRAJOPT_E_INVALID, "trajopt_set_sweep: NULL handle");
+    if ((variant != 0 && variant != 2 && variant != 4) || lanes < 1) return fail(TRAJOPT_E_INVALID, "trajopt_set_sweep: variant must be 0, 2 or 4 and lanes >= 1");
+    h->sweep_variant = variant;
+    h->sweep_lanes = lanes;
     return 0;
 }
 

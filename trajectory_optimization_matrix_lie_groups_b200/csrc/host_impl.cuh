@@ -63,6 +63,9 @@ struct trajopt_handle {
     // Nb / ref_batch are settings that outlive a solve ("set before trajopt_begin"); a compaction moves them with their
     // problems, so the next begin puts them back into the caller's order first (restore_caller_order)
     bool nb_permuted = false, ref_permuted = false;
+    // backward sweep of the 12-dimensional families: 0 = auto (four-warp CTAs while the slots in use fit one wave of
+    // them, two-warp CTAs above), 2 / 4 = always that one; lanes = solver handles sharing this GPU (trajopt_set_sweep)
+    int sweep_variant = 0, sweep_lanes = 1, sms = 148;
     int* d_perm = nullptr;
     void* d_scratch = nullptr;
     size_t scratch_bytes = 0;
@@ -241,10 +244,31 @@ inline int backward_groups() {
     return v;
 }
 
+// Four-warp CTAs (backward4.cuh) are resident two per SM: while the slots that may hold running problems fit ONE wave of
+// them — counting the other solver handles that share the GPU — a launch is bound by the latency of a stage, which four
+// warps cut by ~1.6x; beyond that the two-warp sweep keeps every group of a 16 k batch resident.  Bit-identical results.
+// TRAJOPT_SWEEP=2|4 forces one variant (A/B measurements).
+inline bool use_four_warp_sweep(const trajopt_handle* h) {
+    static const int forced = [] { const char* e = getenv("TRAJOPT_SWEEP"); return e ? atoi(e) : 0; }();
+    const int variant = forced ? forced : h->sweep_variant;
+    if (variant == 4) return true;
+    if (variant == 2) return false;
+    return (long long)h->front * h->sweep_lanes <= (long long)h->sms * 2 * 32;
+}
+
 template <int KIND, bool MS>
 int run_backward(trajopt_handle* h, cudaStream_t s, int it) {
     PhaseTimer t(h, s, PH_BWD);
     if constexpr (!on_so3(KIND)) {
+        if (!use_one_warp_sweep() && use_four_warp_sweep(h)) {
+            constexpr size_t smem4 = B3Smem<KIND>::BYTES;
+            auto launch4 = [&](auto kern) -> int {
+                CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
+                LAUNCH(kern, h->Bp / 32, kB4Threads, smem4, s, h->prm, h->w, it);
+                return 0;
+            };
+            return h->var_horizons ? launch4(k_backward4<KIND, MS, true>) : launch4(k_backward4<KIND, MS, false>);
+        }
         if (!use_one_warp_sweep()) {
             constexpr size_t smem3 = B3Smem<KIND>::BYTES;
             auto launch = [&](auto kern, int groups) -> int {

@@ -3,6 +3,7 @@
 #include "kernels.cuh"
 #include "backward.cuh"
 #include "backward3.cuh"
+#include "backward4.cuh"
 
 namespace trajopt {
 

@@ -26,6 +26,8 @@ class PipelinedSolver:
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.depth = depth
         self.solvers = [make_solver() for _ in range(depth)]
+        for sv in self.solvers:
+            sv.set_sweep(0, depth)        # the lanes share the SMs: each one's sweep picks its CTA shape accordingly
         self.streams = [torch.cuda.Stream(device=self.device) for _ in range(depth)]
         self.pools = [ThreadPoolExecutor(max_workers=1, thread_name_prefix=f"trajopt-lane{i}") for i in range(depth)]
         self.active_depth = depth     # lanes in use (<= depth): submit() goes round-robin over the first `active_depth` lanes

@@ -344,6 +344,10 @@ class BatchSolver:
         """Pack the running problems into the leading slots once running * ratio <= slots in use (min_batch < 0: never)."""
         check(lib.trajopt_set_compaction(self._h, int(min_batch), int(ratio)))
 
+    def set_sweep(self, variant=0, lanes=1):
+        """Backward-sweep mapping: 0 automatic, 2 / 4 = always two- / four-warp CTAs; lanes = solvers sharing this GPU."""
+        check(lib.trajopt_set_sweep(self._h, int(variant), int(lanes)))
+
     def set_profiling(self, on):
         check(lib.trajopt_set_profiling(self._h, int(bool(on))))
 
