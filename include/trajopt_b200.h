@@ -107,6 +107,13 @@ int trajopt_set_params(trajopt_handle* h, const trajopt_params* p);
 /* h_q_ref [N+1][7] (SE3/drone) or [N+1][4] (SO3), h_xi_ref [N+1][6|3]; host pointers, shared by the batch */
 int trajopt_set_reference(trajopt_handle* h, const double* h_q_ref, const double* h_xi_ref);
 
+/* Receding-horizon use (the caller loop of an MPC: the reference's README names it, its scripts solve single horizons only):
+ * a shared reference LONGER than the horizon — n_rows >= N + 1 samples, same row formats as trajopt_set_reference — is
+ * uploaded once, and trajopt_set_reference_offset slides the (N + 1)-sample window the problems track: stage i tracks
+ * sample first_row + i.  No copy per step.  trajopt_set_reference / _batch replace it. */
+int trajopt_set_reference_long(trajopt_handle* h, const double* h_q_ref, const double* h_xi_ref, int64_t n_rows);
+int trajopt_set_reference_offset(trajopt_handle* h, int64_t first_row);
+
 /* One reference per problem (the batch differs in references as well as in initial states): DEVICE pointers,
  * problem-major d_q_ref [B][N+1][7|4], d_xi_ref [B][N+1][6|3].  Replaces the shared reference until the next
  * trajopt_set_reference.  The multiple-shooting initial guess (traopt_controller.py:3123-3136) and the tracking cost

@@ -60,3 +60,35 @@ def test_closed_loop_tracks_and_warm_start_helps():
     # determinism: the same call twice gives bit-identical closed loops
     again = mpc.receding_horizon(kind, "ms", warm_start=True, **common)
     assert np.array_equal(again.xs, warm.xs) and np.array_equal(again.us, warm.us)
+
+
+def test_sliding_reference_window_equals_an_explicit_window():
+    """trajopt_set_reference_long + _offset(t) is the same problem as trajopt_set_reference on samples [t, t + N]."""
+    from trajectory_optimization_matrix_lie_groups_b200 import layout
+    g, kind, Ib, mass, x0 = _setup()
+    B, N, t = 5, 20, 7
+    X0 = gc.perturbed_x0(x0, B, scale=0.02)
+    q_rows = layout.pose_rows(False, g["prob_q_ref"])
+    a, _, _ = gc.make_solver(g, "ms", B, horizon=N, max_iters=6, tol_grad_norm=1e-12)
+    b, _, _ = gc.make_solver(g, "ms", B, horizon=N, max_iters=6, tol_grad_norm=1e-12)
+    a.set_reference(q_rows[t:t + N + 1], g["prob_xi_ref"][t:t + N + 1])
+    b.set_reference_long(q_rows, g["prob_xi_ref"])
+    b.set_reference_offset(t)
+    ra, rb = a.solve(X0), b.solve(X0)
+    for k in ("J", "iters", "status", "xs", "us"):
+        assert np.array_equal(ra[k].cpu().numpy(), rb[k].cpu().numpy()), k
+    with pytest.raises(Exception):
+        b.set_reference_offset(q_rows.shape[0] - N)        # window would run past the last sample
+    b.set_reference_offset(0)
+    a.set_reference(q_rows[:N + 1], g["prob_xi_ref"][:N + 1])
+    assert np.array_equal(a.solve(X0)["us"].cpu().numpy(), b.solve(X0)["us"].cpu().numpy())
+
+
+def test_mpc_reports_its_rate():
+    from trajectory_optimization_matrix_lie_groups_b200 import mpc
+    g, kind, Ib, mass, x0 = _setup()
+    B, N, T = 64, 20, 10
+    res = mpc.receding_horizon(kind, "ms", q_ref=g["prob_q_ref"], xi_ref=g["prob_xi_ref"], x0_rows=gc.perturbed_x0(x0, B, scale=0.01),
+                               N=N, T=T, dt=float(g["prob_dt"]), Ib=Ib, mass=mass, Q=g["prob_Q"], R=g["prob_R"], P=g["prob_P"],
+                               n_iterations=2, tol_grad_norm=1e-9)
+    assert res.seconds > 0 and res.steps_per_second > 0 and res.us.shape == (B, T, 6)

@@ -72,6 +72,8 @@ SYMBOLS = {
     "trajopt_set_params": (_I, [_P, C.POINTER(Params)]),
     "trajopt_set_reference": (_I, [_P, _P, _P]),
     "trajopt_set_reference_batch": (_I, [_P, _P, _P, _P]),
+    "trajopt_set_reference_long": (_I, [_P, _P, _P, C.c_int64]),
+    "trajopt_set_reference_offset": (_I, [_P, C.c_int64]),
     "trajopt_set_horizons": (_I, [_P, _P, _P]),
     "trajopt_solve_stream": (_I, [_P, _P, C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "trajopt_solve_stream_host": (_I, [_P, _P, C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P]),

@@ -146,6 +146,7 @@ int trajopt_destroy(trajopt_handle* h) {
     void* stage[] = {h->s_x0, h->s_us0, h->s_xs, h->s_us, h->s_J, h->s_grad, h->s_def, h->s_iters, h->s_status};
     for (void* p : stage) if (p) cudaFree(p);
     if (h->d_perm) cudaFree(h->d_perm);
+    if (h->d_ref_long) cudaFree(h->d_ref_long);
     if (h->d_scratch) cudaFree(h->d_scratch);
     if (h->h_counters) cudaFreeHost(h->h_counters);
     if (h->h_ints) cudaFreeHost(h->h_ints);
@@ -239,27 +240,26 @@ int trajopt_set_params(trajopt_handle* h, const trajopt_params* p) {
     return 0;
 }
 
-int trajopt_set_reference(trajopt_handle* h, const double* h_q_ref, const double* h_xi_ref) {
-    if (!h || !h_q_ref || !h_xi_ref) return fail(TRAJOPT_E_INVALID, "trajopt_set_reference: NULL argument");
-    DeviceGuard guard(h->device);
+// pack n_rows reference samples into the rows the cost reads (pose, twist, rotation matrix, [p]x R)
+static int pack_reference_rows(const trajopt_handle* h, const double* h_q_ref, const double* h_xi_ref, size_t n_rows, std::vector<double>& rows) {
     const int rr = h->REFROW;
-    std::vector<double> rows((size_t)(h->N + 1) * rr);
-    for (int i = 0; i <= h->N; ++i) {
-        double* r = rows.data() + (size_t)i * rr;
+    rows.assign(n_rows * rr, 0.0);
+    for (size_t i = 0; i < n_rows; ++i) {
+        double* r = rows.data() + i * rr;
         if (on_so3(h->kind)) {
-            const double* q = h_q_ref + (size_t)i * 4;
+            const double* q = h_q_ref + i * 4;
             const double nq = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
             if (!(nq > 0.0)) return fail(TRAJOPT_E_INVALID, "trajopt_set_reference: zero quaternion");
             for (int j = 0; j < 4; ++j) r[j] = q[j] / nq;
-            for (int j = 0; j < 3; ++j) r[4 + j] = h_xi_ref[(size_t)i * 3 + j];
+            for (int j = 0; j < 3; ++j) r[4 + j] = h_xi_ref[i * 3 + j];
             host_quat_to_rot(r, r + 7);
         } else {
-            const double* q = h_q_ref + (size_t)i * 7;
+            const double* q = h_q_ref + i * 7;
             const double nq = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
             if (!(nq > 0.0)) return fail(TRAJOPT_E_INVALID, "trajopt_set_reference: zero quaternion");
             for (int j = 0; j < 4; ++j) r[j] = q[j] / nq;
             for (int j = 0; j < 3; ++j) r[4 + j] = q[4 + j];
-            for (int j = 0; j < 6; ++j) r[7 + j] = h_xi_ref[(size_t)i * 6 + j];
+            for (int j = 0; j < 6; ++j) r[7 + j] = h_xi_ref[i * 6 + j];
             double* R = r + 13;
             host_quat_to_rot(r, R);
             const double* p = r + 4;   // [p]x R
@@ -270,9 +270,49 @@ int trajopt_set_reference(trajopt_handle* h, const double* h_q_ref, const double
             }
         }
     }
+    return 0;
+}
+
+int trajopt_set_reference(trajopt_handle* h, const double* h_q_ref, const double* h_xi_ref) {
+    if (!h || !h_q_ref || !h_xi_ref) return fail(TRAJOPT_E_INVALID, "trajopt_set_reference: NULL argument");
+    DeviceGuard guard(h->device);
+    std::vector<double> rows;
+    int rc = pack_reference_rows(h, h_q_ref, h_xi_ref, (size_t)h->N + 1, rows);
+    if (rc) return rc;
     CUDA_OK(cudaMemcpy(h->d_ref, rows.data(), rows.size() * sizeof(double), cudaMemcpyHostToDevice));
+    h->w.ref = h->d_ref;
+    h->ref_long_rows = 0;
     h->w.ref_batch = nullptr;      // back to the shared reference
     h->have_ref = true;
+    h->begun = false;
+    return 0;
+}
+
+int trajopt_set_reference_long(trajopt_handle* h, const double* h_q_ref, const double* h_xi_ref, int64_t n_rows) {
+    if (!h || !h_q_ref || !h_xi_ref) return fail(TRAJOPT_E_INVALID, "trajopt_set_reference_long: NULL argument");
+    if (n_rows < (int64_t)h->N + 1) return fail(TRAJOPT_E_INVALID, "trajopt_set_reference_long: need at least N + 1 samples");
+    DeviceGuard guard(h->device);
+    std::vector<double> rows;
+    int rc = pack_reference_rows(h, h_q_ref, h_xi_ref, (size_t)n_rows, rows);
+    if (rc) return rc;
+    if (h->d_ref_long) cudaFree(h->d_ref_long);
+    h->d_ref_long = nullptr;
+    CUDA_OK(cudaMalloc((void**)&h->d_ref_long, rows.size() * sizeof(double)));
+    CUDA_OK(cudaMemcpy(h->d_ref_long, rows.data(), rows.size() * sizeof(double), cudaMemcpyHostToDevice));
+    h->ref_long_rows = n_rows;
+    h->w.ref = h->d_ref_long;
+    h->w.ref_batch = nullptr;
+    h->have_ref = true;
+    h->begun = false;
+    return 0;
+}
+
+int trajopt_set_reference_offset(trajopt_handle* h, int64_t first_row) {
+    if (!h) return fail(TRAJOPT_E_INVALID, "trajopt_set_reference_offset: NULL handle");
+    if (!h->ref_long_rows) return fail(TRAJOPT_E_STATE, "trajopt_set_reference_offset: call trajopt_set_reference_long first");
+    if (first_row < 0 || first_row + h->N + 1 > h->ref_long_rows) return fail(TRAJOPT_E_INVALID, "trajopt_set_reference_offset: window out of range");
+    h->w.ref = h->d_ref_long + (size_t)first_row * h->REFROW;
+    h->w.ref_batch = nullptr;
     h->begun = false;
     return 0;
 }

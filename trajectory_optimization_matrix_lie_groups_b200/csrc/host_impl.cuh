@@ -72,6 +72,8 @@ struct trajopt_handle {
     std::vector<void*> allocs;
     void* hist_allocs[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     double* d_ref = nullptr;
+    double* d_ref_long = nullptr;    // trajopt_set_reference_long: a reference longer than the horizon; w.ref points at a window of it
+    int64_t ref_long_rows = 0;
     double* d_ref_batch = nullptr;   // per-problem references, allocated on first use
     double* d_dweight = nullptr;
     int* h_counters = nullptr;   // pinned, written by k_publish4 through its device alias
@@ -628,7 +630,7 @@ int set_reference_batch_impl(trajopt_handle* h, const double* d_q, const double*
 template <int KIND>
 int debug_stage_impl(trajopt_handle* h, int i, int terminal, int n, const double* x, const double* u, double* f,
                      double* Fx, double* Fu, double* l, double* lx, double* lxx, double* lu, double* err, cudaStream_t s) {
-    LAUNCH((k_debug_stage<KIND>), blocks_for(n, 64), 64, 0, s, h->prm, h->d_ref, i, terminal, n, x, u, f, Fx, Fu, l, lx,
+    LAUNCH((k_debug_stage<KIND>), blocks_for(n, 64), 64, 0, s, h->prm, h->w.ref, i, terminal, n, x, u, f, Fx, Fu, l, lx,
            lxx, lu, err);
     return 0;
 }

@@ -118,6 +118,17 @@ class BatchSolver:
             raise ValueError(f"reference shapes {q.shape}, {xi.shape} do not match N={self.N}, kind={self.kind}")
         check(lib.trajopt_set_reference(self._h, q.ctypes.data_as(C.c_void_p), xi.ctypes.data_as(C.c_void_p)))
 
+    def set_reference_long(self, q_ref_rows, xi_ref):
+        """A shared reference longer than the horizon: (n, 7|4) and (n, 6|3), n >= N + 1; `set_reference_offset` slides the window."""
+        q = np.ascontiguousarray(q_ref_rows, dtype=np.float64)
+        xi = np.ascontiguousarray(xi_ref, dtype=np.float64)
+        if q.ndim != 2 or q.shape[1] != self.NS - (self.NX - self.NP) or xi.shape != (q.shape[0], self.NX - self.NP):
+            raise ValueError(f"reference shapes {q.shape}, {xi.shape} do not match kind={self.kind}")
+        check(lib.trajopt_set_reference_long(self._h, q.ctypes.data_as(C.c_void_p), xi.ctypes.data_as(C.c_void_p), q.shape[0]))
+
+    def set_reference_offset(self, first_row):
+        check(lib.trajopt_set_reference_offset(self._h, int(first_row)))
+
     def set_reference_batch(self, q_ref_rows, xi_ref):
         """One reference per problem: q_ref_rows (B, N+1, 7|4) quat[+pos] rows, xi_ref (B, N+1, 6|3)."""
         npose, nv = self.NS - (self.NX - self.NP), self.NX - self.NP
@@ -324,11 +335,14 @@ class BatchSolver:
 
     def stage_eval(self, i, x_rows, u_rows=None, terminal=False, want=("f", "F_x", "F_u", "l", "l_x", "l_xx", "l_u", "err")):
         """The reference's per-stage callbacks on rows of states/controls against reference row i."""
-        x = torch.as_tensor(np.asarray(x_rows, dtype=np.float64)).reshape(-1, self.NS).contiguous().to(self.device)
+        def rows(a, width):      # device tensors pass through; anything else comes up from the host
+            t = a if torch.is_tensor(a) else torch.as_tensor(np.asarray(a, dtype=np.float64))
+            return t.to(self.device, torch.float64).reshape(-1, width).contiguous()
+        x = rows(x_rows, self.NS)
         n = x.shape[0]
         u = None
         if not terminal:
-            u = torch.as_tensor(np.asarray(u_rows, dtype=np.float64)).reshape(-1, self.NU).contiguous().to(self.device)
+            u = rows(u_rows, self.NU)
             if u.shape[0] != n:
                 raise ValueError("x and u row counts differ")
         NX, NU, NS = self.NX, self.NU, self.NS
