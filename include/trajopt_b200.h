@@ -180,6 +180,16 @@ int trajopt_solve_host(trajopt_handle* h, const double* h_x0, const double* h_us
                        double* h_xs, double* h_us, double* h_J, int32_t* h_iters, int32_t* h_status,
                        double* h_grad, double* h_defect, void* stream);
 
+/* The same in two halves: _begin returns a ticket once the solve is complete and every device->host copy is queued (it does
+ * not wait for them, and leaves `stream` free), _wait blocks until the host arrays of that ticket are filled.  The next
+ * _begin on the handle may be issued before the wait: its compute overlaps the previous copies (the reference's joblib
+ * pool overlaps result pickling with the next job the same way, visualization/perturb_all_compute.py:240-250).  Up to 4
+ * tickets may be outstanding per handle; the host arrays of a ticket must stay untouched until its wait returns. */
+int trajopt_solve_host_begin(trajopt_handle* h, const double* h_x0, const double* h_us_init, int us_mode,
+                             double* h_xs, double* h_us, double* h_J, int32_t* h_iters, int32_t* h_status,
+                             double* h_grad, double* h_defect, void* stream, int* ticket_out);
+int trajopt_solve_host_wait(trajopt_handle* h, int ticket);
+
 /* ---- parity-test exports (dense, problem-major) ------------------------------------------- */
 /* linearise the CURRENT trajectory: d_Fx [B][N][NX][NX], d_Fu [B][N][NX][NU], d_defect [B][N][NX],
  * d_L [B][N+1], d_Lx [B][N+1][NX], d_Lxx [B][N+1][NX][NX], d_Lu [B][N][NU]; any may be NULL */

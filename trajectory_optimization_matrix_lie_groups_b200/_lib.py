@@ -87,6 +87,8 @@ SYMBOLS = {
     "trajopt_export_al_state": (_I, [_P, _P, _P, _P]),
     "trajopt_solve": (_I, [_P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
     "trajopt_solve_host": (_I, [_P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "trajopt_solve_host_begin": (_I, [_P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(_I)]),
+    "trajopt_solve_host_wait": (_I, [_P, _I]),
     "trajopt_debug_linearize": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "trajopt_debug_gains": (_I, [_P, _P, _P, _P]),
     "trajopt_debug_linesearch_rows": (_I, [_P]),

@@ -143,7 +143,7 @@ int trajopt_destroy(trajopt_handle* h) {
     DeviceGuard guard(h->device);
     for (void* p : h->allocs) cudaFree(p);
     for (void* p : h->hist_allocs) if (p) cudaFree(p);
-    void* stage[] = {h->s_x0, h->s_us0, h->s_xs, h->s_us, h->s_J, h->s_grad, h->s_def, h->s_iters, h->s_status};
+    void* stage[] = {h->s_x0, h->s_us0, h->s_xs, h->s_us, h->s_J, h->s_grad, h->s_def, h->s_iters, h->s_status, h->s_snap, h->d_late};
     for (void* p : stage) if (p) cudaFree(p);
     if (h->d_perm) cudaFree(h->d_perm);
     if (h->d_ref_long) cudaFree(h->d_ref_long);
@@ -157,6 +157,7 @@ int trajopt_destroy(trajopt_handle* h) {
     if (h->s2) cudaStreamDestroy(h->s2);
     if (h->s_copy) cudaStreamDestroy(h->s_copy);
     for (cudaEvent_t e : h->ev_host) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->ev_done) if (e) cudaEventDestroy(e);
     for (void* p : h->so_buf) if (p) cudaFree(p);
     if (h->so_x0) cudaFree(h->so_x0);
     delete h;
@@ -543,10 +544,23 @@ static bool host_early_copy() {
     return v;
 }
 
-int trajopt_solve_host(trajopt_handle* h, const double* h_x0, const double* h_us_init, int us_mode, double* h_xs,
-                       double* h_us, double* h_J, int32_t* h_iters, int32_t* h_status, double* h_grad, double* h_defect,
-                       void* stream) {
-    if (!h || !h_x0) return fail(TRAJOPT_E_INVALID, "trajopt_solve_host: NULL argument");
+// The host-buffer solve in two halves, so that the device->host copies of one solve can drain while the next one
+// computes on the same handle:
+//   trajopt_solve_host_begin  copies the inputs up, runs the whole solve, queues every device->host copy on the handle's
+//                             copy stream and returns a ticket WITHOUT waiting for them; the caller's stream is left free
+//                             (it never waits for a copy), so the next solve may begin at once;
+//   trajopt_solve_host_wait   blocks until the host arrays of that ticket are complete.
+// Copies and the solves share nothing but the staging arrays: a later solve waits (on the device) for the previous ticket's
+// copies before it rewrites them, which on the headline workload is ~300 ms after they were queued.
+// Order on the copy stream (everything that lands in the host arrays goes through it, in this order):
+//   bulk copy of ALL rows at the moment three quarters of the batch have stopped (finished problems' rows are final; the
+//   running ones' rows are stale and may even be half-rewritten by the final export, which runs beside the copy)
+//   -> rows of the problems that were still running then, written by a kernel straight into the pinned host arrays
+//   -> the per-problem summaries.
+int trajopt_solve_host_begin(trajopt_handle* h, const double* h_x0, const double* h_us_init, int us_mode, double* h_xs,
+                             double* h_us, double* h_J, int32_t* h_iters, int32_t* h_status, double* h_grad, double* h_defect,
+                             void* stream, int* ticket_out) {
+    if (!h || !h_x0 || !ticket_out) return fail(TRAJOPT_E_INVALID, "trajopt_solve_host: NULL argument");
     if (us_mode < 0 || us_mode > 2) return fail(TRAJOPT_E_INVALID, "trajopt_solve_host: us_mode must be 0, 1 or 2");
     if (us_mode != 0 && !h_us_init) return fail(TRAJOPT_E_INVALID, "trajopt_solve_host: us_mode != 0 needs h_us_init");
     DeviceGuard guard(h->device);
@@ -559,6 +573,8 @@ int trajopt_solve_host(trajopt_handle* h, const double* h_x0, const double* h_us
         CUDA_OK(cudaMalloc((void**)&h->s_def, B * 8));
         CUDA_OK(cudaMalloc((void**)&h->s_iters, B * 4));
         CUDA_OK(cudaMalloc((void**)&h->s_status, B * 4));
+        CUDA_OK(cudaMalloc((void**)&h->s_snap, B * 4));
+        CUDA_OK(cudaMalloc((void**)&h->d_late, B * 4));
     }
     if (h_xs && !h->s_xs) CUDA_OK(cudaMalloc((void**)&h->s_xs, B * (N + 1) * h->NS * 8));
     if (h_us && !h->s_us) CUDA_OK(cudaMalloc((void**)&h->s_us, B * N * h->NU * 8));
@@ -569,89 +585,115 @@ int trajopt_solve_host(trajopt_handle* h, const double* h_x0, const double* h_us
         CUDA_OK(cudaMalloc((void**)&h->s_us0, us0_bytes));
         h->s_us0_bytes = us0_bytes;
     }
+    if (!h->s_copy) CUDA_OK(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
+    if (!h->ev_host[0]) {
+        CUDA_OK(cudaEventCreateWithFlags(&h->ev_host[0], cudaEventDisableTiming));
+        CUDA_OK(cudaEventCreateWithFlags(&h->ev_host[1], cudaEventDisableTiming));
+        for (cudaEvent_t& e : h->ev_done) CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming | cudaEventBlockingSync));   // the waiting thread sleeps
+    }
+    const int ticket = h->next_ticket;
+    const cudaEvent_t prev_done = h->tickets_issued ? h->ev_done[(ticket + kHostTickets - 1) % kHostTickets] : nullptr;
+    // the event of this ticket is about to be re-recorded: the ticket that used it kHostTickets solves ago must be complete
+    if (h->tickets_issued >= kHostTickets) CUDA_OK(cudaEventSynchronize(h->ev_done[ticket]));
     CUDA_OK(cudaMemcpyAsync(h->s_x0, h_x0, B * h->NS * 8, cudaMemcpyHostToDevice, s));
     if (us0_bytes) CUDA_OK(cudaMemcpyAsync(h->s_us0, h_us_init, us0_bytes, cudaMemcpyHostToDevice, s));
-    // The solve, with the trajectories of the problems that have already stopped sent home EARLY: once three quarters
-    // of the batch have finished, their rows are final; everything is exported to the staging arrays and copied to the
-    // host on a side stream while the remaining iterations run (on the headline workload: 90 % of 2.4 GB behind the
-    // last seven iterations).  At the end only the rows of the late problems are copied again.
     int rc = trajopt_begin(h, h->s_x0, us0_bytes ? h->s_us0 : nullptr, us_mode, stream);
     if (rc) return rc;
     const int units = (h->method == TRAJOPT_AL_MS) ? h->user.n_al_iters : h->prm.max_iters + 1;
     const bool can_early = (h_xs || h_us) && h->method != TRAJOPT_AL_MS && host_early_copy();
-    bool early = false;
+    bool early = false, staged_wait = false;
     std::vector<int32_t> snap;
-    if (can_early) {
-        if (!h->s_copy) CUDA_OK(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
-        if (!h->ev_host[0]) {
-            CUDA_OK(cudaEventCreateWithFlags(&h->ev_host[0], cudaEventDisableTiming));
-            CUDA_OK(cudaEventCreateWithFlags(&h->ev_host[1], cudaEventDisableTiming));
-        }
-    }
+    // before anything is written into the staging arrays: the previous ticket's copies have read them (device-side wait)
+    auto staging_free = [&]() -> int {
+        if (!staged_wait && prev_done) CUDA_OK(cudaStreamWaitEvent(s, prev_done, 0));
+        staged_wait = true;
+        return 0;
+    };
     int active = 1;
     for (int u = 0; u < units && active != 0; ++u) {
         if ((rc = trajopt_iterate(h, 1, &active, stream))) return rc;
         if (can_early && !early && active > 0 && (size_t)active * 4 <= B) {
-            if ((rc = trajopt_export(h, h_xs ? h->s_xs : nullptr, h_us ? h->s_us : nullptr, nullptr, nullptr, h->s_status, nullptr,
+            if ((rc = staging_free())) return rc;
+            if ((rc = trajopt_export(h, h_xs ? h->s_xs : nullptr, h_us ? h->s_us : nullptr, nullptr, nullptr, h->s_snap, nullptr,
                                      nullptr, stream)))
                 return rc;
-            LAUNCH(k_ints_to_host, blocks_for((int)B, 256), 256, 0, s, (const int*)h->s_status, (volatile int*)h->h_ints_dev, (int)B);
+            LAUNCH(k_ints_to_host, blocks_for((int)B, 256), 256, 0, s, (const int*)h->s_snap, (volatile int*)h->h_ints_dev, (int)B);
             CUDA_OK(cudaEventRecord(h->ev_host[0], s));
             CUDA_OK(cudaStreamWaitEvent(h->s_copy, h->ev_host[0], 0));
             if (h_xs) CUDA_OK(cudaMemcpyAsync(h_xs, h->s_xs, B * (N + 1) * h->NS * 8, cudaMemcpyDeviceToHost, h->s_copy));
             if (h_us) CUDA_OK(cudaMemcpyAsync(h_us, h->s_us, B * N * h->NU * 8, cudaMemcpyDeviceToHost, h->s_copy));
-            CUDA_OK(cudaEventRecord(h->ev_host[1], h->s_copy));
             CUDA_OK(cudaStreamSynchronize(s));
             snap.assign(h->h_ints, h->h_ints + B);
             early = true;
         }
     }
-    if (early) CUDA_OK(cudaStreamWaitEvent(s, h->ev_host[1], 0));   // the staging arrays are about to be rewritten
-    if (early) {   // only the stragglers' rows are new; s_status still holds the snapshot of the early export
-        const int bg = blocks_for(h->Bp, 128);
-        const Work& w = h->w;
-        if (h_xs) LAUNCH(k_export_traj_late, export_grid(h, (h->N + 1) * (h->NS)), 128, 0, s, h->B, h->Bp, h->NS, w.X[0], w.X[1], w.sel, (const int*)w.orig, (const int*)h->s_status, h->s_xs, h->N + 1, h->var_horizons ? (const int*)w.Nb : (const int*)nullptr, 0);
-        if (h_us) LAUNCH(k_export_traj_late, export_grid(h, (h->N) * (h->NU)), 128, 0, s, h->B, h->Bp, h->NU, w.U[0], w.U[1], w.sel, (const int*)w.orig, (const int*)h->s_status, h->s_us, h->N, h->var_horizons ? (const int*)w.Nb : (const int*)nullptr, 1);
+    if ((rc = staging_free())) return rc;
+    const Work& w = h->w;
+    const int* nb = h->var_horizons ? (const int*)w.Nb : (const int*)nullptr;
+    if (early) {   // only the stragglers' rows are new; s_snap holds the status snapshot of the early export
+        if (h_xs) LAUNCH(k_export_traj_late, export_grid(h, (h->N + 1) * (h->NS)), 128, 0, s, h->B, h->Bp, h->NS, w.X[0], w.X[1], w.sel, (const int*)w.orig, (const int*)h->s_snap, h->s_xs, h->N + 1, nb, 0);
+        if (h_us) LAUNCH(k_export_traj_late, export_grid(h, (h->N) * (h->NU)), 128, 0, s, h->B, h->Bp, h->NU, w.U[0], w.U[1], w.sel, (const int*)w.orig, (const int*)h->s_snap, h->s_us, h->N, nb, 1);
     }
     if ((rc = trajopt_export(h, (!early && h_xs) ? h->s_xs : nullptr, (!early && h_us) ? h->s_us : nullptr, h->s_J, h->s_iters,
                              h->s_status, h->s_grad, h->s_def, stream)))
         return rc;
-    if (!early) {
-        if (h_xs) CUDA_OK(cudaMemcpyAsync(h_xs, h->s_xs, B * (N + 1) * h->NS * 8, cudaMemcpyDeviceToHost, s));
-        if (h_us) CUDA_OK(cudaMemcpyAsync(h_us, h->s_us, B * N * h->NU * 8, cudaMemcpyDeviceToHost, s));
-    } else {
-        // the problems that were still running at the early export: their rows go again
-        std::vector<int> late;
+    std::vector<int> late;
+    if (early)
         for (size_t b = 0; b < B; ++b)
             if ((snap[b] & 15) == TRAJOPT_RUNNING) late.push_back((int)b);
-        void *dx = nullptr, *du = nullptr;
-        const bool mapped = (!h_xs || cudaHostGetDevicePointer(&dx, h_xs, 0) == cudaSuccess) &&
-                            (!h_us || cudaHostGetDevicePointer(&du, h_us, 0) == cudaSuccess);
-        if (!mapped) (void)cudaGetLastError();
-        if (mapped && !late.empty()) {          // pinned host arrays: the kernel writes the rows over PCIe itself
-            if (!h->d_perm) CUDA_OK(cudaMalloc((void**)&h->d_perm, (size_t)h->Bp * sizeof(int)));
-            CUDA_OK(cudaMemcpyAsync(h->d_perm, late.data(), late.size() * sizeof(int), cudaMemcpyHostToDevice, s));
-            if (h_xs) LAUNCH(k_rows_to_host, (unsigned)late.size(), 256, 0, s, (const int*)h->d_perm, (size_t)(N + 1) * h->NS, (const double*)h->s_xs, (double*)dx);
-            if (h_us) LAUNCH(k_rows_to_host, (unsigned)late.size(), 256, 0, s, (const int*)h->d_perm, (size_t)N * h->NU, (const double*)h->s_us, (double*)du);
-        } else {
-            const size_t rx = (N + 1) * h->NS * 8, ru = N * h->NU * 8;
-            for (size_t i = 0; i < late.size();) {      // pageable host arrays: one copy per run of consecutive rows
-                size_t e = i + 1;
-                while (e < late.size() && late[e] == late[e - 1] + 1) ++e;
-                const size_t b = (size_t)late[i], n = e - i;
-                if (h_xs) CUDA_OK(cudaMemcpyAsync((char*)h_xs + b * rx, (char*)h->s_xs + b * rx, n * rx, cudaMemcpyDeviceToHost, s));
-                if (h_us) CUDA_OK(cudaMemcpyAsync((char*)h_us + b * ru, (char*)h->s_us + b * ru, n * ru, cudaMemcpyDeviceToHost, s));
-                i = e;
-            }
+    void *dx = nullptr, *du = nullptr;
+    const bool mapped = early && !late.empty() && (!h_xs || cudaHostGetDevicePointer(&dx, h_xs, 0) == cudaSuccess) &&
+                        (!h_us || cudaHostGetDevicePointer(&du, h_us, 0) == cudaSuccess);
+    if (early && !late.empty() && !mapped) (void)cudaGetLastError();
+    if (mapped) CUDA_OK(cudaMemcpyAsync(h->d_late, late.data(), late.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+    // everything the solve produced is in the staging arrays: the rest belongs to the copy stream
+    CUDA_OK(cudaEventRecord(h->ev_host[1], s));
+    CUDA_OK(cudaStreamWaitEvent(h->s_copy, h->ev_host[1], 0));
+    cudaStream_t c = h->s_copy;
+    if (!early) {
+        if (h_xs) CUDA_OK(cudaMemcpyAsync(h_xs, h->s_xs, B * (N + 1) * h->NS * 8, cudaMemcpyDeviceToHost, c));
+        if (h_us) CUDA_OK(cudaMemcpyAsync(h_us, h->s_us, B * N * h->NU * 8, cudaMemcpyDeviceToHost, c));
+    } else if (mapped) {          // pinned host arrays: the kernel writes the stragglers' rows over PCIe itself
+        if (h_xs) LAUNCH(k_rows_to_host, (unsigned)late.size(), 256, 0, c, (const int*)h->d_late, (size_t)(N + 1) * h->NS, (const double*)h->s_xs, (double*)dx);
+        if (h_us) LAUNCH(k_rows_to_host, (unsigned)late.size(), 256, 0, c, (const int*)h->d_late, (size_t)N * h->NU, (const double*)h->s_us, (double*)du);
+    } else {
+        const size_t rx = (N + 1) * h->NS * 8, ru = N * h->NU * 8;
+        for (size_t i = 0; i < late.size();) {      // pageable host arrays: one copy per run of consecutive rows
+            size_t e = i + 1;
+            while (e < late.size() && late[e] == late[e - 1] + 1) ++e;
+            const size_t b = (size_t)late[i], n = e - i;
+            if (h_xs) CUDA_OK(cudaMemcpyAsync((char*)h_xs + b * rx, (char*)h->s_xs + b * rx, n * rx, cudaMemcpyDeviceToHost, c));
+            if (h_us) CUDA_OK(cudaMemcpyAsync((char*)h_us + b * ru, (char*)h->s_us + b * ru, n * ru, cudaMemcpyDeviceToHost, c));
+            i = e;
         }
     }
-    if (h_J) CUDA_OK(cudaMemcpyAsync(h_J, h->s_J, B * 8, cudaMemcpyDeviceToHost, s));
-    if (h_grad) CUDA_OK(cudaMemcpyAsync(h_grad, h->s_grad, B * 8, cudaMemcpyDeviceToHost, s));
-    if (h_defect) CUDA_OK(cudaMemcpyAsync(h_defect, h->s_def, B * 8, cudaMemcpyDeviceToHost, s));
-    if (h_iters) CUDA_OK(cudaMemcpyAsync(h_iters, h->s_iters, B * 4, cudaMemcpyDeviceToHost, s));
-    if (h_status) CUDA_OK(cudaMemcpyAsync(h_status, h->s_status, B * 4, cudaMemcpyDeviceToHost, s));
-    CUDA_OK(cudaStreamSynchronize(s));
+    if (h_J) CUDA_OK(cudaMemcpyAsync(h_J, h->s_J, B * 8, cudaMemcpyDeviceToHost, c));
+    if (h_grad) CUDA_OK(cudaMemcpyAsync(h_grad, h->s_grad, B * 8, cudaMemcpyDeviceToHost, c));
+    if (h_defect) CUDA_OK(cudaMemcpyAsync(h_defect, h->s_def, B * 8, cudaMemcpyDeviceToHost, c));
+    if (h_iters) CUDA_OK(cudaMemcpyAsync(h_iters, h->s_iters, B * 4, cudaMemcpyDeviceToHost, c));
+    if (h_status) CUDA_OK(cudaMemcpyAsync(h_status, h->s_status, B * 4, cudaMemcpyDeviceToHost, c));
+    CUDA_OK(cudaEventRecord(h->ev_done[ticket], c));
+    h->next_ticket = (ticket + 1) % kHostTickets;
+    h->tickets_issued += 1;
+    *ticket_out = ticket;
     return 0;
+}
+
+int trajopt_solve_host_wait(trajopt_handle* h, int ticket) {
+    if (!h) return fail(TRAJOPT_E_INVALID, "trajopt_solve_host_wait: NULL handle");
+    if (ticket < 0 || ticket >= kHostTickets || !h->ev_done[ticket]) return fail(TRAJOPT_E_INVALID, "trajopt_solve_host_wait: no such ticket");
+    DeviceGuard guard(h->device);
+    CUDA_OK(cudaEventSynchronize(h->ev_done[ticket]));
+    return 0;
+}
+
+int trajopt_solve_host(trajopt_handle* h, const double* h_x0, const double* h_us_init, int us_mode, double* h_xs,
+                       double* h_us, double* h_J, int32_t* h_iters, int32_t* h_status, double* h_grad, double* h_defect,
+                       void* stream) {
+    int ticket = -1;
+    int rc = trajopt_solve_host_begin(h, h_x0, h_us_init, us_mode, h_xs, h_us, h_J, h_iters, h_status, h_grad, h_defect, stream, &ticket);
+    if (rc) return rc;
+    return trajopt_solve_host_wait(h, ticket);
 }
 
 int trajopt_debug_linearize(trajopt_handle* h, double* d_Fx, double* d_Fu, double* d_defect, double* d_L, double* d_Lx,

@@ -29,6 +29,7 @@ enum { PH_LIN = 0, PH_BWD = 1, PH_FWD = 2, PH_OTHER = 3, PH_COUNT = 4 };
 using namespace trajopt;
 
 constexpr int kMaxChunks = 32;
+constexpr int kHostTickets = 4;     // host-buffer solves of one handle whose copies may be outstanding at once
 
 struct trajopt_handle {
     int kind = 0, method = 0, N = 0, B = 0, Bp = 0, device = 0;
@@ -48,6 +49,11 @@ struct trajopt_handle {
     std::function<int(int)> stream_progress;   // called once per iteration with the completed prefix of problem ids
     cudaStream_t s_copy = nullptr;              // trajopt_solve_host / _stream_host: device -> host copies beside the solve
     cudaEvent_t ev_host[2] = {nullptr, nullptr};
+    cudaEvent_t ev_done[kHostTickets] = {};     // trajopt_solve_host_begin / _wait: all copies of a ticket have landed
+    int next_ticket = 0;
+    long long tickets_issued = 0;
+    int32_t* s_snap = nullptr;                  // status snapshot of the early export (by caller index)
+    int* d_late = nullptr;                      // rows copied again at the end
     void* so_buf[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // its device staging (xs, us, J, iters, status, grad, defect)
     size_t so_bytes[7] = {0, 0, 0, 0, 0, 0, 0};
     double* so_x0 = nullptr;

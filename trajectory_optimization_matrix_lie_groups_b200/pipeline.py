@@ -30,6 +30,9 @@ class PipelinedSolver:
             sv.set_sweep(0, depth)        # the lanes share the SMs: each one's sweep picks its CTA shape accordingly
         self.streams = [torch.cuda.Stream(device=self.device) for _ in range(depth)]
         self.pools = [ThreadPoolExecutor(max_workers=1, thread_name_prefix=f"trajopt-lane{i}") for i in range(depth)]
+        # host-buffer solves: a second thread per lane waits for the device->host copies of a finished solve while the
+        # lane's own thread already runs the next one (trajopt_solve_host_begin / _wait)
+        self.drains = [ThreadPoolExecutor(max_workers=1, thread_name_prefix=f"trajopt-drain{i}") for i in range(depth)]
         self.active_depth = depth     # lanes in use (<= depth): submit() goes round-robin over the first `active_depth` lanes
         self._next = 0
         self._lock = threading.Lock()
@@ -50,8 +53,15 @@ class PipelinedSolver:
             lane = self._next % max(1, min(self.active_depth, self.depth))
             self._next = (lane + 1) % max(1, min(self.active_depth, self.depth))
         if host:
-            fn = lambda s, *a, **k: s.solve_host(*a, **k)      # noqa: E731
-            return self.pools[lane].submit(self._run, lane, fn, (x0, us_init), dict(trajectories=trajectories, out=out))
+            fn = lambda s, *a, **k: s.solve_host_begin(*a, **k)      # noqa: E731
+            begun = self.pools[lane].submit(self._run, lane, fn, (x0, us_init), dict(trajectories=trajectories, out=out))
+
+            def drain():
+                ticket, res = begun.result()
+                with torch.cuda.device(self.device):
+                    self.solvers[lane].solve_host_wait(ticket)
+                return res
+            return self.drains[lane].submit(drain)
         fn = lambda s, *a, **k: s.solve(*a, **k)               # noqa: E731
         return self.pools[lane].submit(self._run, lane, fn, (x0, us_init), dict(trajectories=trajectories))
 
@@ -62,7 +72,7 @@ class PipelinedSolver:
             yield f.result()
 
     def close(self):
-        for p in self.pools:
+        for p in self.pools + self.drains:
             p.shutdown(wait=True)
         for s in self.solvers:
             s.close()

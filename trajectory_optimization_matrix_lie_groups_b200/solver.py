@@ -283,8 +283,9 @@ class BatchSolver:
                                             hp(out["defect"]), _stream(self.device)))
         return out
 
-    def solve_host(self, x0, us_init=None, trajectories=True, out=None):
-        """Same through HOST buffers (NumPy, ideally pinned): H2D, solve, D2H inside one call."""
+    def solve_host_begin(self, x0, us_init=None, trajectories=True, out=None):
+        """First half of `solve_host`: returns (ticket, out) once the solve is done and the copies into `out` are queued;
+        `solve_host_wait(ticket)` completes them.  The next solve on this handle may begin in between."""
         B, N = self.B, self.N
         x0 = np.ascontiguousarray(x0, dtype=np.float64)
         if x0.shape != (B, self.NS):
@@ -302,9 +303,20 @@ class BatchSolver:
 
         def hp(a):
             return C.c_void_p(0) if a is None else a.ctypes.data_as(C.c_void_p)
-        check(lib.trajopt_solve_host(self._h, x0.ctypes.data_as(C.c_void_p), us_p, mode, hp(out["xs"]), hp(out["us"]),
-                                     hp(out["J"]), hp(out["iters"]), hp(out["status"]), hp(out["grad"]),
-                                     hp(out["defect"]), _stream(self.device)))
+        ticket = C.c_int(-1)
+        self._host_keep = (x0, us_init, out)      # the library reads / writes these until the ticket's wait returns
+        check(lib.trajopt_solve_host_begin(self._h, x0.ctypes.data_as(C.c_void_p), us_p, mode, hp(out["xs"]), hp(out["us"]),
+                                           hp(out["J"]), hp(out["iters"]), hp(out["status"]), hp(out["grad"]),
+                                           hp(out["defect"]), _stream(self.device), C.byref(ticket)))
+        return ticket.value, out
+
+    def solve_host_wait(self, ticket):
+        check(lib.trajopt_solve_host_wait(self._h, int(ticket)))
+
+    def solve_host(self, x0, us_init=None, trajectories=True, out=None):
+        """Same through HOST buffers (NumPy, ideally pinned): H2D, solve, D2H inside one call."""
+        ticket, out = self.solve_host_begin(x0, us_init, trajectories, out)
+        self.solve_host_wait(ticket)
         return out
 
     # ---------------------------------------------------------------------------- parity exports
