@@ -154,6 +154,7 @@ int trajopt_destroy(trajopt_handle* h) {
     if (h->ev[1]) cudaEventDestroy(h->ev[1]);
     for (cudaEvent_t e : h->ev_chunk) if (e) cudaEventDestroy(e);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->ev_block) cudaEventDestroy(h->ev_block);
     if (h->s2) cudaStreamDestroy(h->s2);
     if (h->s_copy) cudaStreamDestroy(h->s_copy);
     for (cudaEvent_t e : h->ev_host) if (e) cudaEventDestroy(e);

@@ -44,6 +44,7 @@ struct trajopt_handle {
     cudaStream_t s2 = nullptr;
     cudaEvent_t ev_chunk[kMaxChunks] = {};
     cudaEvent_t ev_join = nullptr;
+    cudaEvent_t ev_block = nullptr;   // wait_stream: blocking (sleeping) wait when many lanes share the host's cores
     bool lin_ready = false;
     bool streaming = false;      // inside trajopt_solve_stream
     std::function<int(int)> stream_progress;   // called once per iteration with the completed prefix of problem ids
@@ -308,13 +309,26 @@ int run_forward(trajopt_handle* h, cudaStream_t s, int a_lo, int a_cnt, int need
     return 0;
 }
 
+// The once-per-iteration wait of the host loop.  cudaStreamSynchronize spins on a core, which is the lowest latency and
+// fine for a few lanes; with many solver handles per GPU and one process per GPU (8 lanes x 8 ranks on the 32 cores of the
+// measurement box) the spinning threads starve each other, so from six lanes up the thread sleeps on a blocking event.
+inline cudaError_t wait_stream(trajopt_handle* h, cudaStream_t s) {
+    if (h->sweep_lanes < 6) return cudaStreamSynchronize(s);
+    if (!h->ev_block) {
+        cudaError_t e = cudaEventCreateWithFlags(&h->ev_block, cudaEventDisableTiming | cudaEventBlockingSync);
+        if (e != cudaSuccess) return e;
+    }
+    cudaError_t e = cudaEventRecord(h->ev_block, s);
+    return e != cudaSuccess ? e : cudaEventSynchronize(h->ev_block);
+}
+
 // number of problems still running -> host (synchronises the stream)
 inline int count_running(trajopt_handle* h, cudaStream_t s, int* out) {
     PhaseTimer t(h, s, PH_OTHER);
     CUDA_OK(cudaMemsetAsync(h->w.counters, 0, 4 * sizeof(int), s));
     LAUNCH(k_count_running, blocks_for(h->Bp, 128), 128, 0, s, h->prm, h->w);
     LAUNCH(k_publish4, 1, 32, 0, s, (const int*)h->w.counters, (volatile int*)h->h_counters_dev);
-    CUDA_OK(cudaStreamSynchronize(s));
+    CUDA_OK(wait_stream(h, s));
     *out = h->h_counters[0];
     return 0;
 }
