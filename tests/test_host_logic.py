@@ -188,3 +188,25 @@ def test_utilis_converters_and_lie_helpers():
     assert np.array_equal(tu.Jmnf2J(J), P @ J @ P)
     assert tu.is_pos_def(np.eye(3)) and not tu.is_pos_def(-np.eye(3)) and not tu.is_pos_def(np.array([[1.0, 2.0], [0.0, 1.0]]))
     assert abs(tu.SE32absangle(T) - np.rad2deg(np.linalg.norm([0.3, -0.2, 0.9]))) < 1e-10
+
+
+def test_second_order_terms_fail_like_the_reference():
+    """hessians=True: the reference's exact-dynamics classes never define `_f_xx` (traopt_dynamics.py:684-686), so its
+    `fit` dies with AttributeError in `_linearization`; without the flag f_xx raises NotImplementedError (:852-866)."""
+    import pytest
+    from trajectory_optimization_matrix_lie_groups_b200.traoptlibrary import traopt_controller as tc, traopt_cost, traopt_dynamics
+    J = np.diag([0.5, 0.7, 0.9, 1.0, 1.0, 1.0])
+    q_ref, xi_ref = np.tile(np.eye(4), (6, 1, 1)), np.zeros((6, 6))
+    plain = traopt_dynamics.SE3Dynamics(J, 0.01)
+    with pytest.raises(NotImplementedError):
+        plain.f_xx(None, None, 0)
+    dyn = traopt_dynamics.SE3Dynamics(J, 0.01, hessians=True)
+    assert dyn.has_hessians
+    with pytest.raises(AttributeError):
+        dyn.f_xx(None, None, 0)
+    cost = traopt_cost.SE3TrackingQuadraticGaussNewtonCost(np.eye(12), np.eye(6), np.eye(12), q_ref, xi_ref)
+    ctrl = tc.iLQR_Tracking_SE3_MS(dyn, cost, 5, q_ref, xi_ref, hessians=True)
+    with pytest.raises(AttributeError):
+        ctrl.fit([np.eye(4), np.zeros(6)], np.zeros((5, 6)), n_iterations=1)
+    with pytest.warns(UserWarning):
+        tc.iLQR_Tracking_SE3_MS(plain, cost, 5, q_ref, xi_ref, hessians=True)       # :2382-2383

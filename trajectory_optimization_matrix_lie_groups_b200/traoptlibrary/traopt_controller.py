@@ -108,6 +108,10 @@ class _NativeController(BaseController):
         return self.cost.cost if hasattr(self.cost, "constr") else self.cost
 
     def _solver(self, B, device=None, **params):
+        if self._use_hessians:
+            # the reference's `_linearization` calls dynamics.f_xx here (traopt_controller.py:2150-2156, 2890-2896), which
+            # fails for every exact-dynamics class: same error, before anything is solved
+            self.dynamics.f_xx(None, None, 0)
         key = (B, str(device))
         s = self._solvers.get(key)
         cost = self._base_cost()

@@ -98,12 +98,21 @@ class _NativeDynamics(BaseDynamics):
     def f_u(self, x, u, i):
         return self._eval(x, u, ("F_u",))["F_u"]
 
-    def f_xx(self, x, u, i):
-        raise NotImplementedError("second-order dynamics terms are not implemented by the reference's exact models either "
-                                  "(traopt_dynamics.py:852-898)")
+    def _second_order(self, name):
+        """The reference's error behaviour (traopt_dynamics.py:852-898): NotImplementedError without `hessians=True`;
+        with it, the attribute error of a `_f_xx` that the exact models never define (:684-686 is commented out)."""
+        if not self._has_hessians:
+            raise NotImplementedError
+        raise AttributeError(f"'{type(self).__name__}' object has no attribute '_{name}'")
 
-    f_ux = f_xx
-    f_uu = f_xx
+    def f_xx(self, x, u, i):
+        return self._second_order("f_xx")
+
+    def f_ux(self, x, u, i):
+        return self._second_order("f_ux")
+
+    def f_uu(self, x, u, i):
+        return self._second_order("f_uu")
 
 
 class SO3Dynamics(_NativeDynamics):
