@@ -66,6 +66,8 @@ def _oracle_worker(args):
         q_ref = [np.asarray(T, dtype=float) for T in wl.q_ref]
         x0 = [lie.se3_to_matrix(row[:4], row[4:7]), row[7:].copy()]
     us0 = np.zeros((wl.N, dyn.action_size))
+    if n_iters <= 0:                       # whole solve: the script's own iteration cap
+        n_iters = int(wl.solver["max_iters"])
     t0 = time.perf_counter()
     if wl.method == "ss":
         r = solvers.ilqr_ss(dyn, cost, group, wl.N, x0, us0, n_iterations=n_iters, tol_grad_norm=wl.solver["tol_grad_norm"])
@@ -81,15 +83,17 @@ def _oracle_worker(args):
 
 
 def cpu_sample(config, n_iters, iters_per_solve, cores=None):
-    """One bounded CPU sample: one problem per core, `n_iters` DDP iterations each.
+    """One bounded CPU sample: one problem per core, `n_iters` DDP iterations each — or, with n_iters <= 0, WHOLE solves
+    to the script's own stopping rule (no extrapolation: solves per second = problems / pool time).
 
-    Returns (solves_per_second extrapolated to whole solves, cores, description)."""
+    Returns (solves_per_second, cores, description)."""
     import multiprocessing as mp
     # one single-threaded process per core (the reference's joblib sweep); BLAS pools on top of that only oversubscribe
     for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
         os.environ[var] = "1"
     cores = cores or int(os.environ.get("TRAJOPT_BENCH_CORES", "0")) or len(os.sched_getaffinity(0))
     batch = max(cores, 12)
+    whole = n_iters <= 0
     jobs = [(config, b, n_iters, batch) for b in range(cores)]
     t0 = time.perf_counter()
     with mp.get_context("fork").Pool(cores) as pool:
@@ -97,6 +101,13 @@ def cpu_sample(config, n_iters, iters_per_solve, cores=None):
     wall = time.perf_counter() - t0
     done_iters = sum(r[1] for r in res)
     busy = sum(r[0] for r in res)
+    if whole:
+        slowest = max(r[0] for r in res)
+        desc = (f"oracle (NumPy restatement of traoptlibrary) on {cores} processes, 1 problem each (problems 0..{cores - 1} of the "
+                f"workload), WHOLE solves to the script's stopping rule ({done_iters / cores:.1f} iterations on average, "
+                f"{busy / max(done_iters, 1):.2f} s per iteration per core); solves/s = {cores} problems / {slowest:.1f} s (the slowest "
+                f"worker: the pool is done when it is); pool wall {wall:.1f} s")
+        return cores / slowest, cores, desc
     # throughput of the pool in DDP iterations/s, then whole solves = iterations / iters_per_solve
     it_per_s = done_iters / max(r[0] for r in res)
     value = it_per_s / iters_per_solve
@@ -109,7 +120,7 @@ def cpu_sample(config, n_iters, iters_per_solve, cores=None):
 def cpu_sample_subprocess(config, n_iters, iters_per_solve):
     """Run `cpu_sample` in a fresh interpreter (no CUDA context to fork)."""
     proc = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-sample", str(config), str(n_iters),
-                           repr(float(iters_per_solve))], capture_output=True, text=True, timeout=900)
+                           repr(float(iters_per_solve))], capture_output=True, text=True, timeout=600)
     if proc.returncode != 0:
         raise RuntimeError(proc.stderr[-400:])
     d = json.loads(proc.stdout.strip().splitlines()[-1])
@@ -121,8 +132,16 @@ def run_reference_arm(args):
     if rank != 0:
         return 0
     its = float(NOMINAL_ITERS[args.config])
-    n_it = int(os.environ.get("TRAJOPT_BENCH_CPU_ITERS", "2"))
-    if args.warmup > 0:
+    # Each step is a bounded sample of the workload: WHOLE solves of one problem per core when the whole run then fits
+    # ~4 minutes (judged from a one-iteration probe), else the first DDP iterations of each, extrapolated.
+    t_probe = time.perf_counter()
+    cpu_sample(args.config, 1, its)
+    per_iter = time.perf_counter() - t_probe                      # ~ one iteration per core + pool start-up
+    n_it = int(os.environ.get("TRAJOPT_BENCH_CPU_ITERS", "-1"))
+    if n_it < 0:
+        budget = 240.0 / max(args.steps + max(args.warmup - 1, 0), 1)
+        n_it = 0 if per_iter * (its + 4.0) <= budget else max(1, int(budget / per_iter))
+    for _ in range(max(args.warmup - 1, 0)):
         cpu_sample(args.config, 1, its)
     vals, desc, cores = [], "", 0
     t0 = time.perf_counter()
@@ -542,6 +561,20 @@ def run_gpu_arm(args):
                            "< 1e-12 relative); the oracle stops the same problem after 48"}
         s1.close()
 
+    # ---- receding-horizon loop over a batch: closed-loop control steps per second ----
+    mpc_block = None
+    if world == 1 and args.config == 3 and not args.no_latency:
+        from trajectory_optimization_matrix_lie_groups_b200 import mpc
+        Bm, Nm, Tm, itm = 4096, 50, 40, 2
+        kwm = dict(kind=wl.kind, method="ms", q_ref=wl.q_ref, xi_ref=wl.xi_ref, x0_rows=wl.x0_rows[:Bm], N=Nm, dt=wl.dt, Ib=wl.Ib,
+                   mass=wl.mass, Q=wl.Q, R=wl.R, P=wl.P, n_iterations=itm, tol_grad_norm=1e-9, device=dev)
+        mpc.receding_horizon(T=4, **kwm)
+        rm = mpc.receding_horizon(T=Tm, **kwm)
+        mpc_block = {"systems": Bm, "horizon": Nm, "steps": Tm, "ddp_iterations_per_step": itm, "seconds": rm.seconds,
+                     "control_steps_per_s": rm.steps_per_second, "ms_per_step_of_the_batch": 1e3 * rm.seconds / Tm,
+                     "note": "mpc.receding_horizon: warm-started truncated solves + plant step, reference window slid on the device "
+                             "(trajopt_set_reference_long / _offset); state, warm start and the logged loop stay in HBM"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -644,9 +677,13 @@ def run_gpu_arm(args):
                           "note": "at one GPU the strong- and weak-scaling workloads coincide"}
     if latency is not None:
         line["single_solve_latency"] = latency
+    if mpc_block is not None:
+        line["mpc"] = mpc_block
     if world == 1 and not args.no_cpu:
         try:
-            v, cores, desc = cpu_sample_subprocess(args.config, 3, float(iters.mean()) + 1.0)
+            # whole solves of the first `cores` problems (about 10-30 s of CPU work on the box's cores); configs whose solves
+            # are long (AL: thousands of iterations) keep the bounded extrapolated sample
+            v, cores, desc = cpu_sample_subprocess(args.config, 0 if args.config in (2, 3, 5) else 3, float(iters.mean()) + 1.0)
             line["cpu_baseline"] = {"value": v, "unit": "solves/s", "cores": cores, "kind": "port", "sample": desc}
         except Exception as e:   # the baseline is context, never a reason to lose the GPU number
             line["cpu_baseline"] = {"value": None, "unit": "solves/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}

@@ -77,6 +77,8 @@ struct trajopt_handle {
     void* d_scratch = nullptr;
     size_t scratch_bytes = 0;
     std::vector<void*> allocs;
+    std::vector<const void*> smem_ready;   // kernels whose dynamic shared-memory limit has been raised on this handle's device
+    std::vector<int> compact_src;          // maybe_compact: the new order, kept to avoid an allocation per compaction
     void* hist_allocs[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     double* d_ref = nullptr;
     double* d_ref_long = nullptr;    // trajopt_set_reference_long: a reference longer than the horizon; w.ref points at a window of it
@@ -146,6 +148,18 @@ struct PhaseTimer {
 
 inline int blocks_for(int n, int bs) { return (n + bs - 1) / bs; }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize once per kernel and handle (it is a driver call; at B <= 1024 the path is
+// launch bound and it was made before every launch)
+template <typename K>
+int ensure_smem(trajopt_handle* h, K kern, size_t bytes) {
+    const void* key = (const void*)kern;
+    for (const void* p : h->smem_ready)
+        if (p == key) return 0;
+    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    h->smem_ready.push_back(key);
+    return 0;
+}
+
 // host copies of the small algebra needed to pack parameters
 inline void inv3(const double* A, double* Ai) {
     const double a = A[0], b = A[1], c = A[2], d = A[3], e = A[4], f = A[5], g = A[6], hh = A[7], i = A[8];
@@ -214,7 +228,7 @@ inline bool overlap_applies(const trajopt_handle* h) {
 template <int KIND>
 int run_forward_overlapped(trajopt_handle* h, cudaStream_t s, int chunks) {
     constexpr size_t fsmem = FwdSmem<KIND>::BYTES;
-    CUDA_OK(cudaFuncSetAttribute(k_forward_ms_full<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+    { int rc_ = ensure_smem(h, k_forward_ms_full<KIND>, fsmem); if (rc_) return rc_; }
     const int N = h->N;
     // The rollout goes to the handle's own HIGH-PRIORITY stream: its 512 one-warp CTAs are placed first, and the
     // linearisation (caller's stream) fills the registers they leave.  64-thread blocks for the latter: at 254
@@ -272,7 +286,7 @@ int run_backward(trajopt_handle* h, cudaStream_t s, int it) {
         if (!use_one_warp_sweep() && use_four_warp_sweep(h)) {
             constexpr size_t smem4 = B3Smem<KIND>::BYTES;
             auto launch4 = [&](auto kern) -> int {
-                CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
+                { int rc_ = ensure_smem(h, kern, smem4); if (rc_) return rc_; }
                 LAUNCH(kern, h->Bp / 32, kB4Threads, smem4, s, h->prm, h->w, it);
                 return 0;
             };
@@ -282,7 +296,7 @@ int run_backward(trajopt_handle* h, cudaStream_t s, int it) {
             constexpr size_t smem3 = B3Smem<KIND>::BYTES;
             auto launch = [&](auto kern, int groups) -> int {
                 const size_t bytes = groups == 1 ? smem3 : (size_t)groups * B3Smem<KIND>::GROUP_BYTES;
-                CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+                { int rc_ = ensure_smem(h, kern, bytes); if (rc_) return rc_; }
                 LAUNCH(kern, blocks_for(h->Bp / 32, groups), kB3Threads * groups, bytes, s, h->prm, h->w, it);
                 return 0;
             };
@@ -293,7 +307,7 @@ int run_backward(trajopt_handle* h, cudaStream_t s, int it) {
         }
     }
     constexpr size_t smem = (size_t)bwd_smem_doubles<KIND>() * kBlock * sizeof(double);
-    CUDA_OK(cudaFuncSetAttribute(k_backward<KIND, MS, kBlock>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    { int rc_ = ensure_smem(h, k_backward<KIND, MS, kBlock>, smem); if (rc_) return rc_; }
     LAUNCH((k_backward<KIND, MS, kBlock>), h->Bp / kBlock, kBlock, smem, s, h->prm, h->w, it);
     return 0;
 }
@@ -380,7 +394,7 @@ int inner_iteration(trajopt_handle* h, cudaStream_t s) {
                 } else {
                     PhaseTimer t(h, s, PH_FWD);
                     constexpr size_t fsmem = FwdSmem<KIND>::BYTES;
-                    CUDA_OK(cudaFuncSetAttribute(k_forward_ms_full<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+                    { int rc_ = ensure_smem(h, k_forward_ms_full<KIND>, fsmem); if (rc_) return rc_; }
                     LAUNCH((k_forward_ms_full<KIND>), h->Bp / kBlock, kBlock, fsmem, s, h->prm, h->w, 0, h->N);
                 }
                 LAUNCH(k_accept_all, bgrid, 128, 0, s, h->prm, h->w, it);
@@ -458,7 +472,8 @@ inline int maybe_compact(trajopt_handle* h, cudaStream_t s, int act) {
     const int front = h->front;
     if ((long long)act * h->compact_ratio > front || act >= front) return 0;
     PhaseTimer t(h, s, PH_OTHER);
-    std::vector<int> src_of((size_t)front);
+    std::vector<int>& src_of = h->compact_src;
+    src_of.resize((size_t)front);
     LAUNCH(k_ints_to_host, blocks_for(front, 256), 256, 0, s, (const int*)h->w.status, (volatile int*)h->h_ints_dev, front);
     CUDA_OK(cudaStreamSynchronize(s));
     const int* st = h->h_ints;
@@ -529,11 +544,7 @@ int start_inner(trajopt_handle* h, cudaStream_t s, bool al_restart) {
     } else {
         dim3 grid(bgrid, h->N + 1);
         LAUNCH((k_init_ms<KIND>), grid, 128, 0, s, h->prm, h->w, al_restart, (const int*)nullptr);
-        if (h->prm.line_search) {
-            std::vector<double> dw((size_t)h->Bp, h->prm.defect_mu0);
-            CUDA_OK(cudaMemcpyAsync(h->d_dweight, dw.data(), dw.size() * sizeof(double), cudaMemcpyHostToDevice, s));
-            CUDA_OK(cudaStreamSynchronize(s));
-        }
+        if (h->prm.line_search) LAUNCH(k_fill_double, bgrid, 128, 0, s, h->Bp, h->prm.defect_mu0, h->d_dweight);
     }
     h->it = 0;
     h->inner_done = false;

@@ -764,6 +764,10 @@ static __global__ void k_set_horizons(int B, int Bp, int N, const int* __restric
     if (in && b < B) v = min(max(in[b], 1), N);
     out[b] = v;
 }
+static __global__ void k_fill_double(int n, double v, double* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = v;
+}
 static __global__ void k_identity(int n, int* out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = i;
