@@ -91,7 +91,7 @@ int trajopt_create(int kind, int method, int N, int B, int device, trajopt_handl
         const int gl = on_so3(kind) ? GPre<TRAJOPT_SO3>::LEN : GPre<TRAJOPT_SE3>::LEN;
         A_(w.Gpre, (size_t)N * gl * Bp);
     }
-    A_(w.kff, (size_t)N * h->NU * Bp); A_(w.Kfb, (size_t)N * h->NU * h->NX * Bp);
+    A_(w.gains, (size_t)N * (h->NU * h->NX + h->NU) * Bp);
     A_(w.J, Bp); A_(w.grad, Bp); A_(w.dnorm, Bp); A_(w.mu, Bp); A_(w.delta, Bp);
     A_(w.iters, Bp); A_(w.status, Bp); A_(w.ls_state, Bp);
     A_(w.x0, (size_t)h->NS * Bp);
@@ -711,8 +711,10 @@ int trajopt_debug_gains(trajopt_handle* h, double* d_k, double* d_K, void* strea
     DeviceGuard guard(h->device);
     cudaStream_t s = (cudaStream_t)stream;
     const int bg = blocks_for(h->Bp, 128);
-    if (d_k) LAUNCH(k_export_traj, export_grid(h, (h->N) * (h->NU)), 128, 0, s, h->B, h->Bp, h->NU, h->w.kff, h->w.kff, (const int*)nullptr, (const int*)h->w.orig, d_k, h->N, (const int*)nullptr, 0);
-    if (d_K) LAUNCH(k_export_traj, export_grid(h, (h->N) * (h->NU * h->NX)), 128, 0, s, h->B, h->Bp, h->NU * h->NX, h->w.Kfb, h->w.Kfb, (const int*)nullptr, (const int*)h->w.orig, d_K, h->N, (const int*)nullptr, 0);
+    const int glen = h->NU * h->NX + h->NU;
+    const dim3 gg(bg, h->N);
+    if (d_k) LAUNCH(k_export_gains, gg, 128, 0, s, h->B, h->Bp, h->N, glen, h->NU * h->NX, h->NU, (const double*)h->w.gains, (const int*)h->w.orig, d_k);
+    if (d_K) LAUNCH(k_export_gains, gg, 128, 0, s, h->B, h->Bp, h->N, glen, 0, h->NU * h->NX, (const double*)h->w.gains, (const int*)h->w.orig, d_K);
     return 0;
 }
 

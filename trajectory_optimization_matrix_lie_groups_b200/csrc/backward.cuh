@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(LPW) k_backward(const Params prm, Work w, int 
                 kk[r] = s * Lc[r * NU + r];
             }
 #pragma unroll
-            for (int a = 0; a < NU; ++a) w.kff[soa(i, a, NU, (int)Bp, b)] = -kk[a];
+            for (int a = 0; a < NU; ++a) w.gains[lsoa(i, GainRec<KIND>::KFF_OFF + a, GainRec<KIND>::LEN, N, b)] = -kk[a];
         }
 
         // (7) column blocks of 3
@@ -439,7 +439,7 @@ __global__ void __launch_bounds__(LPW) k_backward(const Params prm, Work w, int 
                     kk[r] = s * Lc[r * NU + r];
                 }
 #pragma unroll
-                for (int a = 0; a < NU; ++a) w.Kfb[soa(i, a * NX + CB * 3 + j, NU * NX, (int)Bp, b)] = -kk[a];
+                for (int a = 0; a < NU; ++a) w.gains[lsoa(i, a * NX + CB * 3 + j, GainRec<KIND>::LEN, N, b)] = -kk[a];
                 // V_x(i)[c] = Q_x[c] - Y[:,c]^T y
                 double s = Vxs[(CB * 3 + j) * LPW];
 #pragma unroll

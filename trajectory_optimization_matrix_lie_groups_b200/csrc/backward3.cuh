@@ -197,7 +197,7 @@ template <int KIND, int CB, bool Y_TO_SMEM, bool Y_TO_REGS>
 TO_DEV void b3_gains(const Params& prm, const double* __restrict__ rec, const double (&X)[Dims<KIND>::NX][3],
                      const double (&Lc)[Dims<KIND>::NU * Dims<KIND>::NU], const double (&y)[Dims<KIND>::NU], double mu_used,
                      double (&yq)[3], double* __restrict__ Ys, double (&Yk)[Dims<KIND>::NU][3], double* __restrict__ Kout,
-                     size_t Bp, bool act) {
+                     bool act) {
     using D = Dims<KIND>;
     constexpr int NX = D::NX, NP = D::NP, NU = D::NU, NV = NX - NP, NB = NX / 3, NYC = B3Smem<KIND>::NYC;
 #pragma unroll
@@ -245,7 +245,7 @@ TO_DEV void b3_gains(const Params& prm, const double* __restrict__ rec, const do
         }
         if (act) {
 #pragma unroll
-            for (int a = 0; a < NU; ++a) Kout[(size_t)(a * NX + CB * 3 + j) * Bp] = -kk[a];
+            for (int a = 0; a < NU; ++a) Kout[(a * NX + CB * 3 + j) * kRecStride] = -kk[a];
         }
         double s = 0.0;
 #pragma unroll
@@ -642,13 +642,13 @@ __global__ void __launch_bounds__(kB3Threads * G, 4 / G) k_backward3(const Param
                 }
                 if (live) {
 #pragma unroll
-                    for (int a = 0; a < NU; ++a) w.kff[soa(i, a, NU, (int)Bp, b)] = -kk[a];
+                    for (int a = 0; a < NU; ++a) w.gains[lsoa(i, GainRec<KIND>::KFF_OFF + a, GainRec<KIND>::LEN, N, b)] = -kk[a];
                 }
             }
         }
 
         B3_FENCE();
-        double* Kout = w.Kfb + soa(i, 0, NU * NX, (int)Bp, b);
+        double* Kout = w.gains + lsoa(i, 0, GainRec<KIND>::LEN, N, b);
         double Yk[NU][3];   // Y_2 in registers (warp 0)
 
         if (warp == 0) {
@@ -659,7 +659,7 @@ __global__ void __launch_bounds__(kB3Threads * G, 4 / G) k_backward3(const Param
                 for (int j = 0; j < 3; ++j) vx0[j] = grec[(size_t)(LR::LX_OFF + j) * kRecStride];
                 b3_compute_X<KIND, 0, NP, NX>(Vs, rec, X);
                 B3_FENCE();
-                b3_gains<KIND, 0, true, false>(prm, rec, X, Lc, y, mu_used, yq, Ys, Yk, Kout, Bp, live);
+                b3_gains<KIND, 0, true, false>(prm, rec, X, Lc, y, mu_used, yq, Ys, Yk, Kout, live);
                 B3_FENCE();
                 b3_qx_A<KIND, 0>(Vxs, rec, vx0);
                 if constexpr (MS) b3_qx_Xd<KIND, NP, NX>(rec, X, vx0);
@@ -677,7 +677,7 @@ __global__ void __launch_bounds__(kB3Threads * G, 4 / G) k_backward3(const Param
             for (int j = 0; j < 3; ++j) vx2[j] = grec[(size_t)(LR::LX_OFF + 6 + j) * kRecStride];
             b3_compute_X<KIND, 2, NP, NX>(Vs, rec, X);
             B3_FENCE();
-            b3_gains<KIND, 2, false, true>(prm, rec, X, Lc, y, mu_used, yq, Ys, Yk, Kout, Bp, live);
+            b3_gains<KIND, 2, false, true>(prm, rec, X, Lc, y, mu_used, yq, Ys, Yk, Kout, live);
             B3_FENCE();
             b3_qx_A<KIND, 2>(Vxs, rec, vx2);
             if constexpr (MS) b3_qx_Xd<KIND, NP, NX>(rec, X, vx2);
@@ -719,7 +719,7 @@ __global__ void __launch_bounds__(kB3Threads * G, 4 / G) k_backward3(const Param
                 for (int j = 0; j < 3; ++j) vx1[j] = grec[(size_t)(LR::LX_OFF + 3 + j) * kRecStride];
                 b3_compute_X<KIND, 1, NP, NX>(Vs, rec, X);
                 B3_FENCE();
-                b3_gains<KIND, 1, true, false>(prm, rec, X, Lc, y, mu_used, yq, Ys, Yk, Kout, Bp, live);
+                b3_gains<KIND, 1, true, false>(prm, rec, X, Lc, y, mu_used, yq, Ys, Yk, Kout, live);
                 B3_FENCE();
                 b3_qx_A<KIND, 1>(Vxs, rec, vx1);
                 if constexpr (MS) b3_qx_Xd<KIND, NP, NX>(rec, X, vx1);
@@ -738,7 +738,7 @@ __global__ void __launch_bounds__(kB3Threads * G, 4 / G) k_backward3(const Param
             for (int j = 0; j < 3; ++j) vx3[j] = grec[(size_t)(LR::LX_OFF + 9 + j) * kRecStride];
             b3_compute_X<KIND, 3, NP, NX>(Vs, rec, X);
             B3_FENCE();
-            b3_gains<KIND, 3, true, false>(prm, rec, X, Lc, y, mu_used, yq, Ys, Yk, Kout, Bp, live);
+            b3_gains<KIND, 3, true, false>(prm, rec, X, Lc, y, mu_used, yq, Ys, Yk, Kout, live);
             B3_FENCE();
             b3_qx_A<KIND, 3>(Vxs, rec, vx3);
             if constexpr (MS) b3_qx_Xd<KIND, NP, NX>(rec, X, vx3);

@@ -51,7 +51,7 @@ TO_DEV void b4_column(const Params& prm, const Work& w, double* __restrict__ Vs,
     for (int j = 0; j < 3; ++j) vx[j] = grec[(size_t)(LR::LX_OFF + CB * 3 + j) * kRecStride];
     b3_compute_X<KIND, CB, NP, NX>(Vs, rec, X);
     B4_FENCE();
-    b3_gains<KIND, CB, !Y_REGS, Y_REGS>(prm, rec, X, Lc, y, mu_used, yq, Ys, Yk, Kout, Bp, live);
+    b3_gains<KIND, CB, !Y_REGS, Y_REGS>(prm, rec, X, Lc, y, mu_used, yq, Ys, Yk, Kout, live);
     B4_FENCE();
     b3_qx_A<KIND, CB>(Vxs, rec, vx);
     if constexpr (MS) b3_qx_Xd<KIND, NP, NX>(rec, X, vx);
@@ -332,13 +332,13 @@ __global__ void __launch_bounds__(kB4Threads, 2) k_backward4(const Params prm, W
                 }
                 if (live) {
 #pragma unroll
-                    for (int a = 0; a < NU; ++a) w.kff[soa(i, a, NU, (int)Bp, b)] = -kk[a];
+                    for (int a = 0; a < NU; ++a) w.gains[lsoa(i, GainRec<KIND>::KFF_OFF + a, GainRec<KIND>::LEN, N, b)] = -kk[a];
                 }
             }
         }
 
         B4_FENCE();
-        double* Kout = w.Kfb + soa(i, 0, NU * NX, (int)Bp, b);
+        double* Kout = w.gains + lsoa(i, 0, GainRec<KIND>::LEN, N, b);
         if (warp == 0) {
             b4_column<KIND, MS, VH, 0>(prm, w, Vs, Vxs, Ys, rec, grec, Lc, y, mu_used, Kout, Bp, live, i, b);
             if constexpr (!MS) if (vlive) {

@@ -54,6 +54,19 @@ template <int KIND> struct LinRec {
     static constexpr int LEN = LXX_OFF + LXX_LEN;
 };
 
+// Gains of the backward sweep (what the rollouts read): group-major like the linearisation records,
+//   [group of 32 problems][stage][field][32],   fields: K (NU x NX, row-major) then k (NU),
+// so the gains of one stage of one warp's 32 problems are ONE contiguous chunk of LEN * 256 bytes: the rollout stages them
+// with a single TMA bulk copy per stage.  (Round 1 kept them as [stage][field][Bp] and issued one 256-byte bulk copy per
+// field: `cp.async.bulk` takes uniform registers, so 84 copies with lane-varying addresses compile into a loop that
+// elects one lane at a time — ncu attributed 48 % of the rollout's stall samples to that loop.)
+template <int KIND> struct GainRec {
+    using D = Dims<KIND>;
+    static constexpr int K_OFF = 0;
+    static constexpr int KFF_OFF = D::NU * D::NX;
+    static constexpr int LEN = KFF_OFF + D::NU;
+};
+
 // ------------------------------------------------------------------------------------------
 // Parameter block, passed to every kernel by value (lives in the constant bank).
 // ------------------------------------------------------------------------------------------

@@ -24,8 +24,7 @@ struct Work {
     double* Lc;          // [N+1][Bp] stage costs of the current trajectory
     double* Dsq;         // [N][Bp]   squared defect norm per stage
     double* Gpre;        // [N][GPre::LEN][Bp]  MS: x(i+1) Exp(d_i) f(x_i,u_i)^-1 (pose) and f(x_i,u_i).xi of the current trajectory
-    double* kff;         // [N][NU][Bp]
-    double* Kfb;         // [N][NU*NX][Bp]
+    double* gains;       // [Bp/32][N][GainRec::LEN][32]  feedback gains K and feedforward terms k (group-major, see GainRec)
     double* J;           // [Bp] cost of the current trajectory (J_opt)
     double* Jcand;       // [n_alphas][Bp] candidate costs of the line search
     double* grad;        // [Bp]

@@ -76,9 +76,9 @@ __global__ void __launch_bounds__(kBlock) k_forward(const Params prm, Work w, in
 #pragma unroll
         for (int a = 0; a < NU; ++a) {
             u[a] = U[soa(i, a, NU, Bp, b)];
-            double s = alpha * w.kff[soa(i, a, NU, Bp, b)];
+            double s = alpha * w.gains[lsoa(i, GainRec<KIND>::KFF_OFF + a, GainRec<KIND>::LEN, N, b)];
 #pragma unroll
-            for (int c = 0; c < NX; ++c) s += w.Kfb[soa(i, a * NX + c, NU * NX, Bp, b)] * dx[c];
+            for (int c = 0; c < NX; ++c) s += w.gains[lsoa(i, a * NX + c, GainRec<KIND>::LEN, N, b)] * dx[c];
             du[a] = s;
             unew[a] = u[a] + s;
         }
@@ -188,27 +188,26 @@ __global__ void __launch_bounds__(kBlock) k_forward(const Params prm, Work w, in
 // ------------------------------------------------------------------------------------------
 // The hot rollout: multiple shooting, rollout='nonlinear', full step (alpha = 1), written to the other
 // buffer, no cost (the next linearisation evaluates it).  One warp per 32 problems, the horizon runs
-// sequentially inside the thread.  Per stage the gains K_i (NU x NX), k_i and u_i of the warp's 32
-// problems are staged in shared memory, double-buffered, by TMA bulk copies issued two stages ahead
-// (one 256-byte row per field, spread over the lanes; mbarrier completion), so the recursion never
-// waits on HBM for them; G_i and f(x_i,u_i).xi come precomputed from the linearisation (GPre).
+// sequentially inside the thread.  Per stage the gains K_i (NU x NX) and k_i of the warp's 32 problems
+// — one contiguous chunk of the group-major gain array (GainRec) — are staged in shared memory,
+// double-buffered, by ONE TMA bulk copy issued two stages ahead (mbarrier completion), so the recursion
+// never waits on HBM for them; u_i, G_i and f(x_i,u_i).xi (precomputed by the linearisation, GPre) are
+// loaded at the top of the stage, before the chain needs them.
 //   dx = x_new(i) (-) x(i);  u_new = u + k + K dx;  f_new = f(x_new, u_new)
 //   q_new(i+1) = G_i f_new.q;  xi_new(i+1) = xi(i+1) + f_new.xi - f.xi + d_xi          (:2697-2718)
 // ------------------------------------------------------------------------------------------
 template <int KIND> struct FwdSmem {
-    using D = Dims<KIND>;
-    static constexpr int K_OFF = 0;
-    static constexpr int KFF_OFF = D::NU * D::NX;
-    static constexpr int U_OFF = KFF_OFF + D::NU;
-    static constexpr int FIELDS = U_OFF + D::NU;
-    static constexpr int BUF_DOUBLES = FIELDS * 32;
-    static constexpr size_t BYTES = (size_t)2 * BUF_DOUBLES * 8 + 16;
+    using GR = GainRec<KIND>;
+    static constexpr int BUF_DOUBLES = GR::LEN * 32;                     // one stage of gains of 32 problems
+    static constexpr uint32_t BUF_BYTES = (uint32_t)BUF_DOUBLES * 8;
+    static constexpr size_t BYTES = (size_t)2 * BUF_BYTES + 16;          // double buffer + two mbarriers
 };
 
 template <int KIND>
 __global__ void __launch_bounds__(kBlock) k_forward_ms_full(const Params prm, Work w, int i0, int i1) {
     using D = Dims<KIND>;
     using LR = LinRec<KIND>;
+    using GR = GainRec<KIND>;
     using FS = FwdSmem<KIND>;
     constexpr int NX = D::NX, NP = D::NP, NU = D::NU, NV = NX - NP, F = LR::LEN;
     constexpr int GL = GPre<KIND>::LEN, GP = GPre<KIND>::NPOSE;
@@ -223,11 +222,6 @@ __global__ void __launch_bounds__(kBlock) k_forward_ms_full(const Params prm, Wo
     const double* U = w.U[cur];
     double* Xn = w.X[1 - cur];
     double* Un = w.U[1 - cur];
-    // The u rows are copied for the whole group from ONE buffer: the one the running problems use (they have
-    // all flipped once per iteration).  Should running lanes ever disagree, u is read per lane instead.
-    const unsigned actmask = __ballot_sync(0xffffffffu, act);
-    const int cur_run = __shfl_sync(0xffffffffu, cur, __ffs(actmask) - 1);
-    const bool mixed = __ballot_sync(0xffffffffu, act && cur != cur_run) != 0u;
     const uint32_t bar0 = b3_smem_addr(fsm + 2 * FS::BUF_DOUBLES);
     const uint32_t bar1 = bar0 + 8;
     if (lane == 0) {
@@ -235,23 +229,11 @@ __global__ void __launch_bounds__(kBlock) k_forward_ms_full(const Params prm, Wo
         b3_mbar_init(bar1, 1);
     }
     __syncwarp();
-    const int b0 = blockIdx.x * kBlock;   // first problem of the group: rows of 32 lanes are contiguous in every SoA array
+    // the gains of stage s of this warp's 32 problems: one contiguous chunk (GainRec), one bulk copy by one lane
+    const double* gains0 = w.gains + lsoa(0, 0, GR::LEN, N, b - lane);
     auto issue = [&](int stage, int buf) {
-        const uint32_t dst = b3_smem_addr(fsm + buf * FS::BUF_DOUBLES);
-        const uint32_t bar = buf ? bar1 : bar0;
-        const int nf = mixed ? FS::U_OFF : FS::FIELDS;
-        if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(nf * 256) : "memory");
-        __syncwarp();
-        for (int f = lane; f < nf; f += 32) {
-            const double* src;
-            if (f < FS::KFF_OFF) src = w.Kfb + soa(stage, f, NU * NX, Bp, b0);
-            else if (f < FS::U_OFF) src = w.kff + soa(stage, f - FS::KFF_OFF, NU, Bp, b0);
-            else src = w.U[cur_run] + soa(stage, f - FS::U_OFF, NU, Bp, b0);
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                             dst + (uint32_t)f * 256u),
-                         "l"(src), "r"(256u), "r"(bar)
-                         : "memory");
-        }
+        if (lane == 0)
+            b3_tma_load(b3_smem_addr(fsm + buf * FS::BUF_DOUBLES), gains0 + (size_t)stage * FS::BUF_DOUBLES, FS::BUF_BYTES, buf ? bar1 : bar0);
     };
     // stages [i0, i1) of the horizon: the whole of it, or one chunk (run_forward_overlapped), resuming from x_new(i0)
     issue(i0, i0 & 1);
@@ -272,7 +254,7 @@ __global__ void __launch_bounds__(kBlock) k_forward_ms_full(const Params prm, Wo
         const bool live = act && (i < Nb);
         // independent of the recursion: issue these loads first
         load_state<KIND>(X, i + 1, Bp, b, xnext);
-        double G[GP], fxi[NV], dxi[NV];
+        double G[GP], fxi[NV], dxi[NV], u[NU];
         {
             const double* gp = w.Gpre + soa(i, 0, GL, Bp, b);
 #pragma unroll
@@ -281,6 +263,8 @@ __global__ void __launch_bounds__(kBlock) k_forward_ms_full(const Params prm, Wo
             for (int j = 0; j < NV; ++j) fxi[j] = gp[(size_t)(GP + j) * Bp];
 #pragma unroll
             for (int j = 0; j < NV; ++j) dxi[j] = w.lin[lsoa(i, LR::D_OFF + NP + j, F, N + 1, b)];
+#pragma unroll
+            for (int a = 0; a < NU; ++a) u[a] = U[soa(i, a, NU, Bp, b)];
         }
         double dx[NX];
         state_minus<KIND>(xnew, x, dx);
@@ -290,11 +274,10 @@ __global__ void __launch_bounds__(kBlock) k_forward_ms_full(const Params prm, Wo
 #pragma unroll
         for (int a = 0; a < NU; ++a) {
             // same order as k_forward: s = alpha k (alpha = 1), then += K[a][c] dx[c] for c ascending
-            double s = sb[(FS::KFF_OFF + a) * 32];
+            double s = sb[(GR::KFF_OFF + a) * 32];
 #pragma unroll
-            for (int c = 0; c < NX; ++c) s += sb[(FS::K_OFF + a * NX + c) * 32] * dx[c];
-            const double u = mixed ? U[soa(i, a, NU, Bp, b)] : sb[(FS::U_OFF + a) * 32];
-            unew[a] = u + s;
+            for (int c = 0; c < NX; ++c) s += sb[(GR::K_OFF + a * NX + c) * 32] * dx[c];
+            unew[a] = u[a] + s;
         }
         __syncwarp();                       // every lane is done with this buffer
         if (i + 2 < i1) issue(i + 2, buf);
@@ -426,9 +409,9 @@ __global__ void __launch_bounds__(kBlock) k_ms_expected(const Params prm, Work w
         double du[NU];
 #pragma unroll
         for (int a = 0; a < NU; ++a) {
-            double s = w.kff[soa(i, a, NU, Bp, b)];
+            double s = w.gains[lsoa(i, GainRec<KIND>::KFF_OFF + a, GainRec<KIND>::LEN, N, b)];
 #pragma unroll
-            for (int c = 0; c < NX; ++c) s += w.Kfb[soa(i, a * NX + c, NU * NX, Bp, b)] * dx[c];
+            for (int c = 0; c < NX; ++c) s += w.gains[lsoa(i, a * NX + c, GainRec<KIND>::LEN, N, b)] * dx[c];
             du[a] = s;
         }
         // first / second order terms
@@ -712,6 +695,16 @@ static __global__ void k_export_traj_late(int B, int Bp, int F, const double* s0
     const int e_own = Nb ? min(len, (Nb[b] - nb_shift + 1) * F) : len;
     double* dst = out + (size_t)o * len;
     for (int e = e0 + lane; e < e1; e += 32) dst[e] = (e < e_own ? src : s0 + b)[(size_t)e * Bp];
+}
+// gains (group-major, GainRec): fields [f0, f0 + nf) of every stage -> out[orig[b]][stage][f - f0]   (grid.y = stage)
+static __global__ void k_export_gains(int B, int Bp, int N, int LEN, int f0, int nf, const double* __restrict__ gains,
+                                      const int* __restrict__ orig, double* __restrict__ out) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const int stage = blockIdx.y;
+    if (b >= Bp) return;
+    const int o = orig[b];
+    if (o >= B) return;
+    for (int f = 0; f < nf; ++f) out[((size_t)o * N + stage) * nf + f] = gains[lsoa(stage, f0 + f, LEN, N, b)];
 }
 // out[orig[b]][row] = src[row][b]
 template <typename T>
