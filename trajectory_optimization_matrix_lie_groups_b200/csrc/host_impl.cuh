@@ -316,10 +316,11 @@ template <int KIND, bool MS, bool WRITE, bool COST>
 int run_forward(trajopt_handle* h, cudaStream_t s, int a_lo, int a_cnt, int need, int from_state) {
     PhaseTimer t(h, s, PH_FWD);
     const int grid = blocks_for(h->Bp * a_cnt, kBlock);
+    constexpr size_t fsmem = FwdSmem<KIND>::BYTES;       // < 48 KB: no attribute needed
     if (h->prm.rollout_linear)
-        LAUNCH((k_forward<KIND, MS, true, WRITE, COST>), grid, kBlock, 0, s, h->prm, h->w, a_lo, a_cnt, need, from_state);
+        LAUNCH((k_forward<KIND, MS, true, WRITE, COST>), grid, kBlock, fsmem, s, h->prm, h->w, a_lo, a_cnt, need, from_state);
     else
-        LAUNCH((k_forward<KIND, MS, false, WRITE, COST>), grid, kBlock, 0, s, h->prm, h->w, a_lo, a_cnt, need, from_state);
+        LAUNCH((k_forward<KIND, MS, false, WRITE, COST>), grid, kBlock, fsmem, s, h->prm, h->w, a_lo, a_cnt, need, from_state);
     return 0;
 }
 

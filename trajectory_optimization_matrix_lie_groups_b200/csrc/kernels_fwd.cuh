@@ -33,23 +33,38 @@ TO_DEV double al_state_value(const Params& prm, const Work& w, int stage, int Bp
     return al_box_terms<NV>(prm.xlb, prm.xub, xi, lam, imu, t1, t2);
 }
 
+// shared memory of the rollouts: the gains of one stage of 32 problems (GainRec), double-buffered
+template <int KIND> struct FwdSmem {
+    using GR = GainRec<KIND>;
+    static constexpr int BUF_DOUBLES = GR::LEN * 32;                     // one stage of gains of 32 problems
+    static constexpr uint32_t BUF_BYTES = (uint32_t)BUF_DOUBLES * 8;
+    static constexpr size_t BYTES = (size_t)2 * BUF_BYTES + 16;          // double buffer + two mbarriers
+};
+
 template <int KIND, bool MS, bool LINEAR, bool WRITE, bool COST>
 __global__ void __launch_bounds__(kBlock) k_forward(const Params prm, Work w, int a_lo, int a_cnt, int need,
                                                     int use_ls_state_as_alpha) {
     using D = Dims<KIND>;
     using LR = LinRec<KIND>;
+    using GR = GainRec<KIND>;
+    using FS = FwdSmem<KIND>;
     constexpr int NX = D::NX, NP = D::NP, NU = D::NU, NV = NX - NP, F = LR::LEN;
-    const int t = blockIdx.x * kBlock + threadIdx.x;
+    extern __shared__ __align__(128) double fsm[];
+    const int lane = threadIdx.x;
+    const int t = blockIdx.x * kBlock + lane;
     const int Bp = prm.Bp, N = prm.N;
+    // a block is 32 consecutive threads and Bp is a multiple of 32: its lanes are 32 consecutive problems (one gain group)
+    // with the same candidate index t / Bp
     const int b = t % Bp;
     int ai = a_lo + t / Bp;
-    if (t / Bp >= a_cnt || b >= prm.B) return;
-    if (w.status[b] != TRAJOPT_RUNNING) return;
-    if (need >= -1 && w.ls_state[b] != need && !use_ls_state_as_alpha) return;
-    if (use_ls_state_as_alpha) {
+    bool run = (t / Bp < a_cnt) && (b < prm.B) && (w.status[b] == TRAJOPT_RUNNING);
+    if (run && need >= -1 && w.ls_state[b] != need && !use_ls_state_as_alpha) run = false;
+    if (run && use_ls_state_as_alpha) {
         ai = w.ls_state[b];
-        if (ai < a_lo) return;       // a_lo = 1: step size 0 was already written by the first pass
+        if (ai < a_lo) run = false;  // a_lo = 1: step size 0 was already written by the first pass
     }
+    const unsigned runmask = __ballot_sync(0xffffffffu, run);
+    if (runmask == 0u) return;
     // alpha = 1.1 ** (-ai**2)  (:1908, :2472); index 0 is exactly 1.0
     const double alpha = (ai == 0) ? 1.0 : pow(1.1, -(double)(ai * ai));
 
@@ -60,14 +75,39 @@ __global__ void __launch_bounds__(kBlock) k_forward(const Params prm, Work w, in
     double* Un = w.U[1 - cur];
     const double* lin = w.lin;
 
+    // gains of the warp's 32 problems, one stage at a time, double-buffered by one TMA bulk copy per stage (as in
+    // k_forward_ms_full); the lanes that do not run keep the warp's staging company
+    const uint32_t bar0 = b3_smem_addr(fsm + 2 * FS::BUF_DOUBLES);
+    const uint32_t bar1 = bar0 + 8;
+    if (lane == 0) {
+        b3_mbar_init(bar0, 1);
+        b3_mbar_init(bar1, 1);
+    }
+    __syncwarp();
+    const double* gains0 = w.gains + lsoa(0, 0, GR::LEN, N, b - lane);
+    auto issue = [&](int stage, int buf) {
+        if (lane == 0)
+            b3_tma_load(b3_smem_addr(fsm + buf * FS::BUF_DOUBLES), gains0 + (size_t)stage * FS::BUF_DOUBLES, FS::BUF_BYTES, buf ? bar1 : bar0);
+    };
+    uint32_t ph0 = 0, ph1 = 0;
+
     State<KIND> xnew, x, xnext;
     load_state<KIND>(X, 0, Bp, b, x);
     xnew = x;
-    if (WRITE) store_state<KIND>(Xn, 0, Bp, b, xnew);
+    if (WRITE && run) store_state<KIND>(Xn, 0, Bp, b, xnew);
     double J = 0.0, dsq = 0.0;
     const int Nb = w.Nb[b];              // this problem's horizon (<= N)
+    int Nmax = run ? Nb : 0;             // stages the warp stays together for
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) Nmax = max(Nmax, __shfl_xor_sync(0xffffffffu, Nmax, o));
+    issue(0, 0);
+    if (Nmax > 1) issue(1, 1);
 
-    for (int i = 0; i < Nb; ++i) {
+    for (int i = 0; i < Nmax; ++i) {
+        const int buf = i & 1;
+        if (buf) { b3_mbar_wait(bar1, ph1); ph1 ^= 1u; } else { b3_mbar_wait(bar0, ph0); ph0 ^= 1u; }
+        const double* sb = fsm + buf * FS::BUF_DOUBLES + lane;
+        if (run && i < Nb) {
         double refrow[RefRow<KIND>::N];
         if (COST) fetch_ref_row<KIND>(w, Bp, i, b, refrow);
         double dx[NX];
@@ -76,9 +116,9 @@ __global__ void __launch_bounds__(kBlock) k_forward(const Params prm, Work w, in
 #pragma unroll
         for (int a = 0; a < NU; ++a) {
             u[a] = U[soa(i, a, NU, Bp, b)];
-            double s = alpha * w.gains[lsoa(i, GainRec<KIND>::KFF_OFF + a, GainRec<KIND>::LEN, N, b)];
+            double s = alpha * sb[(GR::KFF_OFF + a) * 32];
 #pragma unroll
-            for (int c = 0; c < NX; ++c) s += w.gains[lsoa(i, a * NX + c, GainRec<KIND>::LEN, N, b)] * dx[c];
+            for (int c = 0; c < NX; ++c) s += sb[(GR::K_OFF + a * NX + c) * 32] * dx[c];
             du[a] = s;
             unew[a] = u[a] + s;
         }
@@ -174,8 +214,11 @@ __global__ void __launch_bounds__(kBlock) k_forward(const Params prm, Work w, in
         if (WRITE) store_state<KIND>(Xn, i + 1, Bp, b, xn1);
         xnew = xn1;
         x = xnext;
+        }   // run && i < Nb
+        __syncwarp();                       // every lane is done with this buffer
+        if (i + 2 < Nmax) issue(i + 2, buf);
     }
-    if (COST) {
+    if (COST && run) {
         double refrow[RefRow<KIND>::N];
         fetch_ref_row<KIND>(w, Bp, Nb, b, refrow);
         J = J + stage_cost<KIND>(prm, xnew, nullptr, refrow, true);
@@ -196,13 +239,6 @@ __global__ void __launch_bounds__(kBlock) k_forward(const Params prm, Work w, in
 //   dx = x_new(i) (-) x(i);  u_new = u + k + K dx;  f_new = f(x_new, u_new)
 //   q_new(i+1) = G_i f_new.q;  xi_new(i+1) = xi(i+1) + f_new.xi - f.xi + d_xi          (:2697-2718)
 // ------------------------------------------------------------------------------------------
-template <int KIND> struct FwdSmem {
-    using GR = GainRec<KIND>;
-    static constexpr int BUF_DOUBLES = GR::LEN * 32;                     // one stage of gains of 32 problems
-    static constexpr uint32_t BUF_BYTES = (uint32_t)BUF_DOUBLES * 8;
-    static constexpr size_t BYTES = (size_t)2 * BUF_BYTES + 16;          // double buffer + two mbarriers
-};
-
 template <int KIND>
 __global__ void __launch_bounds__(kBlock) k_forward_ms_full(const Params prm, Work w, int i0, int i1) {
     using D = Dims<KIND>;
