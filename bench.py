@@ -363,11 +363,13 @@ class Leg:
         """one batch alone on the GPU -> (ms max over ranks, result)"""
         torch = self.torch
         self.barrier()
+        self.solver.set_sweep(0, 1)             # nothing else shares the GPU now: let the sweep pick its CTA shape for that
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s0.record()
         out1 = self.solver.solve(self.x0_dev, trajectories=False)
         s1.record()
         torch.cuda.synchronize(self.dev)
+        self.solver.set_sweep(0, self.depth)
         ms = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device=self.dev)
         if self.world > 1:
             self.dist.all_reduce(ms, op=self.dist.ReduceOp.MAX)
