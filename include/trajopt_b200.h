@@ -232,9 +232,10 @@ int trajopt_set_profiling(trajopt_handle* h, int enable);
 int trajopt_set_compaction(trajopt_handle* h, int min_batch, int ratio);
 
 /* Backward sweep of the SE3 / quadrotor / rigid-body families (_backward_pass, traopt_controller.py:2178-2261 / 2912-3006):
- * variant 0 = automatic (CTAs of four warps per 32 problems while the slots in use fit one wave of them on the device,
- * counting `lanes` solver handles that share it; CTAs of two warps above), 2 / 4 = always that variant.  The variants are
- * bit-identical; this only changes how a launch maps onto the SMs.  Defaults 0, 1. */
+ * variant 0 = automatic (CTAs of six warps per 32 problems while the slots in use are at most one group per SM, counting
+ * `lanes` solver handles that share the device; CTAs of four warps up to two groups per SM; CTAs of two warps above),
+ * 2 / 4 / 6 = always that variant.  The variants are bit-identical; this only changes how a launch maps onto the SMs.
+ * Defaults 0, 1. */
 int trajopt_set_sweep(trajopt_handle* h, int variant, int lanes);
 
 #ifdef __cplusplus

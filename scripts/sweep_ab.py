@@ -1,8 +1,8 @@
-"""Development probe (GPU): the two backward-sweep mappings side by side.
+"""Development probe (GPU): the backward-sweep mappings side by side.
 
     python scripts/sweep_ab.py [config] [batch]
 
-Solves one batch alone with the sweep forced to two-warp CTAs, forced to four-warp CTAs and chosen automatically;
+Solves one batch alone with the sweep forced to two-, four-, six-warp CTAs and chosen automatically;
 prints the solve time, the per-phase device time of a profiled solve, and checks that every result is bit-identical."""
 import sys
 import time
@@ -19,7 +19,7 @@ wl = workloads.CONFIGS[cfg](B=B)
 s, x0 = wl.make_solver(B=B, device=torch.device("cuda", 0))
 x0d = torch.as_tensor(x0, device="cuda")
 ref = None
-for variant in (2, 4, 0):
+for variant in (2, 4, 6, 0):
     s.set_sweep(variant, 1)
     s.solve(x0d, trajectories=False)
     torch.cuda.synchronize()

@@ -140,17 +140,18 @@ def test_overlapped_rollout_path_at_small_sizes():
     assert proc.returncode == 0, proc.stdout[-2000:] + proc.stderr[-1000:]
 
 
-def test_two_warp_sweep_at_small_sizes():
-    """Below ~9.5 k problems the backward sweep runs as four-warp CTAs (backward4.cuh), so the rest of this suite exercises
+@pytest.mark.parametrize("shape", ["2", "4"])
+def test_other_sweeps_at_small_sizes(shape):
+    """Below ~4.7 k problems the backward sweep runs as six-warp CTAs (backward6.cuh), so the rest of this suite exercises
     that mapping; here the golden replays, the variant tests and the per-problem horizons run with the two-warp sweep of the
-    full-size batches forced (TRAJOPT_SWEEP=2, read once per process: hence the subprocess).  tests/test_gpu_fullsize.py and
-    scripts/sweep_ab.py check that the two mappings are bit-identical."""
+    full-size batches and with the four-warp sweep of the mid-size ones forced (TRAJOPT_SWEEP=2|4, read once per process:
+    hence the subprocess).  tests/test_gpu_fullsize.py and scripts/sweep_ab.py check that the mappings are bit-identical."""
     import os
     import subprocess
     import sys
-    env = dict(os.environ, TRAJOPT_SWEEP="2")
+    env = dict(os.environ, TRAJOPT_SWEEP=shape)
     here = os.path.dirname(os.path.abspath(__file__))
-    proc = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", "-k", "not overlapped_rollout_path and not two_warp_sweep",
+    proc = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", "-k", "not overlapped_rollout_path and not other_sweeps",
                            os.path.join(here, "test_gpu_golden.py"), os.path.join(here, "test_gpu_variants.py"),
                            os.path.join(here, "test_gpu_horizons.py")],
                           env=env, capture_output=True, text=True, timeout=900, cwd=os.path.dirname(here))
@@ -158,13 +159,14 @@ def test_two_warp_sweep_at_small_sizes():
 
 
 def test_sweep_mappings_are_bit_identical():
-    """two-warp, four-warp and automatic choice of the sweep's CTA shape on one handle: every export is bit-identical"""
+    """two-warp, four-warp, six-warp and automatic choice of the sweep's CTA shape on one handle: every export is
+    bit-identical (multiple shooting, single shooting with its adjoint gradient, per-problem horizons, AL with bounds)"""
     g = problems.load_golden("drone_n150")
     B = 70
     s, x0, N = gc.make_solver(g, "ms", B, max_iters=30, tol_grad_norm=1e-12)
     X0 = gc.perturbed_x0(x0, B, scale=0.02)
     ref = None
-    for variant in (2, 4, 0):
+    for variant in (2, 4, 6, 0):
         s.set_sweep(variant, 1)
         out = {k: v.cpu().numpy() for k, v in s.solve(X0).items()}
         out.update({k: v.cpu().numpy() for k, v in s.export_hist().items()})
@@ -174,11 +176,21 @@ def test_sweep_mappings_are_bit_identical():
             ref = out
         for k in ref:
             assert np.array_equal(ref[k], out[k]), (variant, k)
+    s.set_horizons([N - 5 * (b % 7) for b in range(B)])          # per-problem horizons: the VH instantiations
+    ref = None
+    for variant in (2, 4, 6):
+        s.set_sweep(variant, 1)
+        out = {k: v.cpu().numpy() for k, v in s.solve(X0).items()}
+        out.update({k: v.cpu().numpy() for k, v in s.export_hist().items()})
+        if ref is None:
+            ref = out
+        for k in ref:
+            assert np.array_equal(ref[k], out[k]), ("horizons", variant, k)
     g = problems.load_golden("se3_n120")
     s, x0, N = gc.make_solver(g, "ss", 5, max_iters=30, tol_grad_norm=1e-12)
     X0 = gc.perturbed_x0(x0, 5, scale=0.02)
     ref = None
-    for variant in (2, 4):
+    for variant in (2, 4, 6):
         s.set_sweep(variant, 1)
         out = {k: v.cpu().numpy() for k, v in s.solve(X0).items()}
         out.update({k: v.cpu().numpy() for k, v in s.export_hist().items()})

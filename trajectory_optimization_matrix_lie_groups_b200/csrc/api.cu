@@ -812,7 +812,7 @@ int trajopt_set_compaction(trajopt_handle* h, int min_batch, int ratio) {
 
 int trajopt_set_sweep(trajopt_handle* h, int variant, int lanes) {
     if (!h) return fail(TRAJOPT_E_INVALID, "trajopt_set_sweep: NULL handle");
-    if ((variant != 0 && variant != 2 && variant != 4) || lanes < 1) return fail(TRAJOPT_E_INVALID, "trajopt_set_sweep: variant must be 0, 2 or 4 and lanes >= 1");
+    if ((variant != 0 && variant != 2 && variant != 4 && variant != 6) || lanes < 1) return fail(TRAJOPT_E_INVALID, "trajopt_set_sweep: variant must be 0, 2, 4 or 6 and lanes >= 1");
     h->sweep_variant = variant;
     h->sweep_lanes = lanes;
     return 0;

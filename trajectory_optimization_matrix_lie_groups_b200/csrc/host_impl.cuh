@@ -70,8 +70,9 @@ struct trajopt_handle {
     // Nb / ref_batch are settings that outlive a solve ("set before trajopt_begin"); a compaction moves them with their
     // problems, so the next begin puts them back into the caller's order first (restore_caller_order)
     bool nb_permuted = false, ref_permuted = false;
-    // backward sweep of the 12-dimensional families: 0 = auto (four-warp CTAs while the slots in use fit one wave of
-    // them, two-warp CTAs above), 2 / 4 = always that one; lanes = solver handles sharing this GPU (trajopt_set_sweep)
+    // backward sweep of the 12-dimensional families: 0 = auto (six-warp CTAs while the slots in use fit one wave of them,
+    // four-warp CTAs up to one wave of those, two-warp CTAs above), 2 / 4 / 6 = always that one; lanes = solver handles
+    // sharing this GPU (trajopt_set_sweep)
     int sweep_variant = 0, sweep_lanes = 1, sms = 148;
     int* d_perm = nullptr;
     void* d_scratch = nullptr;
@@ -271,19 +272,34 @@ inline int backward_groups() {
 // them — counting the other solver handles that share the GPU — a launch is bound by the latency of a stage, which four
 // warps cut by ~1.6x; beyond that the two-warp sweep keeps every group of a 16 k batch resident.  Bit-identical results.
 // TRAJOPT_SWEEP=2|4 forces one variant (A/B measurements).
-inline bool use_four_warp_sweep(const trajopt_handle* h) {
+// Six-warp CTAs (backward6.cuh: the serial part of a stage on its own two warps beside the column work) are resident one
+// per SM: they are the sweep while the slots in use fit ONE such wave (148 x 32 problems: a single solve, a strong-scaling
+// shard, the last tail iterations).  TRAJOPT_SWEEP=2|4|6 forces one variant (A/B measurements).
+inline int sweep_shape(const trajopt_handle* h) {
     static const int forced = [] { const char* e = getenv("TRAJOPT_SWEEP"); return e ? atoi(e) : 0; }();
     const int variant = forced ? forced : h->sweep_variant;
-    if (variant == 4) return true;
-    if (variant == 2) return false;
-    return (long long)h->front * h->sweep_lanes <= (long long)h->sms * 2 * 32;
+    if (variant == 2 || variant == 4 || variant == 6) return variant;
+    const long long slots = (long long)h->front * h->sweep_lanes;
+    if (slots <= (long long)h->sms * 32) return 6;
+    if (slots <= (long long)h->sms * 2 * 32) return 4;
+    return 2;
 }
 
 template <int KIND, bool MS>
 int run_backward(trajopt_handle* h, cudaStream_t s, int it) {
     PhaseTimer t(h, s, PH_BWD);
     if constexpr (!on_so3(KIND)) {
-        if (!use_one_warp_sweep() && use_four_warp_sweep(h)) {
+        const int shape = use_one_warp_sweep() ? 1 : sweep_shape(h);
+        if (shape == 6) {
+            constexpr size_t smem6 = B6Smem<KIND>::BYTES;
+            auto launch6 = [&](auto kern) -> int {
+                { int rc_ = ensure_smem(h, kern, smem6); if (rc_) return rc_; }
+                LAUNCH(kern, h->Bp / 32, kB6Threads, smem6, s, h->prm, h->w, it);
+                return 0;
+            };
+            return h->var_horizons ? launch6(k_backward6<KIND, MS, true>) : launch6(k_backward6<KIND, MS, false>);
+        }
+        if (shape == 4) {
             constexpr size_t smem4 = B3Smem<KIND>::BYTES;
             auto launch4 = [&](auto kern) -> int {
                 { int rc_ = ensure_smem(h, kern, smem4); if (rc_) return rc_; }
@@ -292,7 +308,7 @@ int run_backward(trajopt_handle* h, cudaStream_t s, int it) {
             };
             return h->var_horizons ? launch4(k_backward4<KIND, MS, true>) : launch4(k_backward4<KIND, MS, false>);
         }
-        if (!use_one_warp_sweep()) {
+        if (shape == 2) {
             constexpr size_t smem3 = B3Smem<KIND>::BYTES;
             auto launch = [&](auto kern, int groups) -> int {
                 const size_t bytes = groups == 1 ? smem3 : (size_t)groups * B3Smem<KIND>::GROUP_BYTES;

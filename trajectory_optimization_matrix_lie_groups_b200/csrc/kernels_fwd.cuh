@@ -4,6 +4,7 @@
 #include "backward.cuh"
 #include "backward3.cuh"
 #include "backward4.cuh"
+#include "backward6.cuh"
 
 namespace trajopt {
 

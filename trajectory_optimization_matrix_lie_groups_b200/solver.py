@@ -371,7 +371,7 @@ class BatchSolver:
         check(lib.trajopt_set_compaction(self._h, int(min_batch), int(ratio)))
 
     def set_sweep(self, variant=0, lanes=1):
-        """Backward-sweep mapping: 0 automatic, 2 / 4 = always two- / four-warp CTAs; lanes = solvers sharing this GPU."""
+        """Backward-sweep mapping: 0 automatic, 2 / 4 / 6 = always two- / four- / six-warp CTAs; lanes = solvers sharing this GPU."""
         check(lib.trajopt_set_sweep(self._h, int(variant), int(lanes)))
 
     def set_profiling(self, on):
