@@ -29,13 +29,28 @@
 
 namespace trajopt {
 
-// Compiler-only fence between the sections of a stage (-DB3_USE_FENCE): stops nvcc from keeping shared-memory operands of
-// one section alive in registers for a later one.  Measured on B200 (16384 x 955): spills 580 -> 424 bytes per thread, but
-// the sweep gets 3 % SLOWER (10.46 against 10.16 ms): the values it kept were cheaper than their reloads.  Off.
-#ifdef B3_USE_FENCE
+// Section marks of a stage.  They are NAMED BARRIERS among the warps of a CTA that run the same code (B3_FENCE: the warps of
+// one role across the CTA's groups; B3_FENCE_ALL: every warp, in the replicated serial part).  Two effects, measured on
+// B200 (16384 x 955, ncu): (1) ptxas does not move instructions across a BAR, so each section is scheduled on its own and
+// the live ranges stay short: 580 bytes of spills per thread -> 0, long-scoreboard stalls 1.25 -> 0.50 cycles per issued
+// instruction, 10.85 -> 9.68 ms per sweep (bit-identical: only the order of independent instructions changes);
+// (2) the warps stay within a few hundred instructions of each other, so a line of the ~110 KB stage body is fetched from
+// beyond the SM once for all of them.  A compiler-only fence (asm volatile("" ::: "memory"), -DB3_USE_FENCE) at the same
+// points does NOT have effect (1) — ptxas still interleaves the sections: 412 bytes of spills, 3 % slower than no fence.
+// -DB3_NO_LOCKSTEP removes the marks (A/B).
+#if defined(B3_NO_LOCKSTEP) && defined(B3_USE_FENCE)
 #define B3_FENCE() asm volatile("" ::: "memory")
-#else
+#define B3_FENCE_ALL() asm volatile("" ::: "memory")
+#elif defined(B3_NO_LOCKSTEP)
 #define B3_FENCE()
+#define B3_FENCE_ALL()
+#else
+#define B3_FENCE()                                                                       \
+    do {                                                                                 \
+        if (warp == 0) asm volatile("bar.sync 1, %0;" ::"r"(lock_role) : "memory");     \
+        else asm volatile("bar.sync 2, %0;" ::"r"(lock_role) : "memory");               \
+    } while (0)
+#define B3_FENCE_ALL() asm volatile("bar.sync 3, %0;" ::"r"(lock_all) : "memory")
 #endif
 constexpr int kB3Warps = 2;
 constexpr int kB3Threads = kB3Warps * 32;
@@ -466,10 +481,14 @@ __global__ void __launch_bounds__(kB3Threads * G, 4 / G) k_backward3(const Param
         act = flags[lane] != 0;
         alive = __ballot_sync(0xffffffffu, act) != 0u;
     }
+    [[maybe_unused]] int lock_role = 32, lock_all = 64;     // threads behind a role-wide / CTA-wide section mark (B3_FENCE)
     if constexpr (G == 1) {
         if (!alive) return;
     } else {
-        if (!__syncthreads_or(alive)) return;
+        const int n_alive = __syncthreads_count(alive && tid == 0);   // groups of this CTA that take part in the sweep
+        if (n_alive == 0) return;
+        lock_role = 32 * n_alive;
+        lock_all = 64 * n_alive;
     }
     if (alive && tid == 0) b3_tma_load(rec_addr, group_base + (size_t)(N - 1) * kStageDoubles, SM::REC_BYTES, bar);
 
@@ -545,6 +564,7 @@ __global__ void __launch_bounds__(kB3Threads * G, 4 / G) k_backward3(const Param
                         for (int c = a; c < NU; ++c) Quu0[a * NU + c] = fma(prm.Bv[r * NU + a], T[c], Quu0[a * NU + c]);
                     }
             }
+            B3_FENCE_ALL();
             // regularisation loop (:2221-2246 / :2964-2991): Cholesky of Q_uu0 + mu B^T B
             while (true) {
                 mu_used = mu;
@@ -591,7 +611,7 @@ __global__ void __launch_bounds__(kB3Threads * G, 4 / G) k_backward3(const Param
             }
         }
 
-        B3_FENCE();
+        B3_FENCE_ALL();
         b3_mbar_wait(bar, parity);   // the stage's record prefix is in shared memory
         parity ^= 1u;
 
@@ -647,7 +667,7 @@ __global__ void __launch_bounds__(kB3Threads * G, 4 / G) k_backward3(const Param
             }
         }
 
-        B3_FENCE();
+        B3_FENCE_ALL();
         double* Kout = w.gains + lsoa(i, 0, GainRec<KIND>::LEN, N, b);
         double Yk[NU][3];   // Y_2 in registers (warp 0)
 
@@ -706,8 +726,10 @@ __global__ void __launch_bounds__(kB3Threads * G, 4 / G) k_backward3(const Param
                 double acc[3][3];
                 b3_block_cb<KIND, 0, 2, false, true>(prm, rec, grec, X, Ys, Yk, acc);
                 b3_store_block<KIND, 0, 2>(Vs, acc, vlive);
+                B3_FENCE();
                 b3_block_cb<KIND, 1, 2, false, true>(prm, rec, grec, X, Ys, Yk, acc);
                 b3_store_block<KIND, 1, 2>(Vs, acc, vlive);
+                B3_FENCE();
                 b3_block_rb<KIND, 2, 3, true, false>(prm, rec, grec, X, Ys, Yk, acc);
                 b3_store_block<KIND, 2, 3>(Vs, acc, vlive);
             }
@@ -768,6 +790,7 @@ __global__ void __launch_bounds__(kB3Threads * G, 4 / G) k_backward3(const Param
                 double acc[3][3];
                 b3_block_cb<KIND, 0, 3, false, false>(prm, rec, grec, X, Ys, Yk, acc);
                 b3_store_block<KIND, 0, 3>(Vs, acc, vlive);
+                B3_FENCE();
                 b3_block_cb<KIND, 1, 3, false, false>(prm, rec, grec, X, Ys, Yk, acc);
                 b3_store_block<KIND, 1, 3>(Vs, acc, vlive);
             }

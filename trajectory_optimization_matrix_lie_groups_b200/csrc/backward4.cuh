@@ -25,12 +25,14 @@
 
 namespace trajopt {
 
-// Compiler-only fence between the sections of a stage: without it nvcc keeps the record / V operands of one section alive
-// for later ones and this kernel spills 1.9 KB per thread instead of 0.5 KB (-DB4_NO_FENCE for the A/B).
+// Section marks of a stage, as in k_backward3: named barriers (one per warp inside its column block, CTA-wide in the
+// replicated serial part) that ptxas does not schedule across.  -DB4_NO_FENCE removes them (A/B).
 #ifdef B4_NO_FENCE
-#define B4_FENCE()
+#define B4_FENCE_COL(CB)
+#define B4_FENCE_ALL()
 #else
-#define B4_FENCE() asm volatile("" ::: "memory")
+#define B4_FENCE_COL(CB) asm volatile("bar.sync %0, 32;" ::"n"(1 + (CB)) : "memory")
+#define B4_FENCE_ALL() asm volatile("bar.sync 5, 128;" ::: "memory")
 #endif
 constexpr int kB4Warps = 4;
 constexpr int kB4Threads = kB4Warps * 32;
@@ -50,17 +52,17 @@ TO_DEV void b4_column(const Params& prm, const Work& w, double* __restrict__ Vs,
 #pragma unroll
     for (int j = 0; j < 3; ++j) vx[j] = grec[(size_t)(LR::LX_OFF + CB * 3 + j) * kRecStride];
     b3_compute_X<KIND, CB, NP, NX>(Vs, rec, X);
-    B4_FENCE();
+    B4_FENCE_COL(CB);
     b3_gains<KIND, CB, !Y_REGS, Y_REGS>(prm, rec, X, Lc, y, mu_used, yq, Ys, Yk, Kout, live);
-    B4_FENCE();
+    B4_FENCE_COL(CB);
     b3_qx_A<KIND, CB>(Vxs, rec, vx);
     if constexpr (MS) b3_qx_Xd<KIND, NP, NX>(rec, X, vx);
-    B4_FENCE();
+    B4_FENCE_COL(CB);
     b3_compute_X<KIND, CB, 0, NP>(Vs, rec, X);
     if constexpr (MS) b3_qx_Xd<KIND, 0, NP>(rec, X, vx);
 #pragma unroll
     for (int j = 0; j < 3; ++j) vx[j] -= yq[j];
-    B4_FENCE();
+    B4_FENCE_COL(CB);
     b3_block_cb<KIND, CB, CB, Y_REGS, Y_REGS>(prm, rec, grec, X, Ys, Yk, hd);
     if constexpr (CB >= 2) {
         if (prm.has_state_bounds) {
@@ -81,16 +83,16 @@ TO_DEV void b4_column(const Params& prm, const Work& w, double* __restrict__ Vs,
     } else if constexpr (CB == 2) {
         b3_block_cb<KIND, 0, 2, false, true>(prm, rec, grec, X, Ys, Yk, acc);
         b3_store_block<KIND, 0, 2>(Vs, acc, vlive4);
-        B4_FENCE();
+        B4_FENCE_COL(CB);
         b3_block_cb<KIND, 1, 2, false, true>(prm, rec, grec, X, Ys, Yk, acc);
         b3_store_block<KIND, 1, 2>(Vs, acc, vlive4);
-        B4_FENCE();
+        B4_FENCE_COL(CB);
         b3_block_rb<KIND, 2, 3, true, false>(prm, rec, grec, X, Ys, Yk, acc);
         b3_store_block<KIND, 2, 3>(Vs, acc, vlive4);
     } else if constexpr (CB == 3) {
         b3_block_cb<KIND, 0, 3, false, false>(prm, rec, grec, X, Ys, Yk, acc);
         b3_store_block<KIND, 0, 3>(Vs, acc, vlive4);
-        B4_FENCE();
+        B4_FENCE_COL(CB);
         b3_block_cb<KIND, 1, 3, false, false>(prm, rec, grec, X, Ys, Yk, acc);
         b3_store_block<KIND, 1, 3>(Vs, acc, vlive4);
     }
@@ -238,7 +240,7 @@ __global__ void __launch_bounds__(kB4Threads, 2) k_backward4(const Params prm, W
                         for (int c = a; c < NU; ++c) Quu0[a * NU + c] = fma(prm.Bv[r * NU + a], T[c], Quu0[a * NU + c]);
                     }
             }
-            B4_FENCE();
+            B4_FENCE_ALL();
             while (true) {   // regularisation loop (:2221-2246 / :2964-2991): Cholesky of Q_uu0 + mu B^T B
                 mu_used = mu;
                 bool pd = true;
@@ -281,7 +283,7 @@ __global__ void __launch_bounds__(kB4Threads, 2) k_backward4(const Params prm, W
             }
         }
 
-        B4_FENCE();
+        B4_FENCE_ALL();
         b3_mbar_wait(bar, parity);   // the stage's record prefix is in shared memory
         parity ^= 1u;
 
@@ -337,7 +339,7 @@ __global__ void __launch_bounds__(kB4Threads, 2) k_backward4(const Params prm, W
             }
         }
 
-        B4_FENCE();
+        B4_FENCE_ALL();
         double* Kout = w.gains + lsoa(i, 0, GainRec<KIND>::LEN, N, b);
         if (warp == 0) {
             b4_column<KIND, MS, VH, 0>(prm, w, Vs, Vxs, Ys, rec, grec, Lc, y, mu_used, Kout, Bp, live, i, b);

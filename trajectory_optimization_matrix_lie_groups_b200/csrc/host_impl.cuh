@@ -319,6 +319,9 @@ int run_backward(trajopt_handle* h, cudaStream_t s, int it) {
             if (h->var_horizons) return launch(k_backward3<KIND, MS, true, 1>, 1);
             const int groups = backward_groups();
             if (groups == 2) return launch(k_backward3<KIND, MS, false, 2>, 2);
+#ifdef B3_WITH_G4
+            if (groups == 4) return launch(k_backward3<KIND, MS, false, 4>, 4);
+#endif
             return launch(k_backward3<KIND, MS, false, 1>, 1);
         }
     }
