@@ -238,6 +238,14 @@ int trajopt_set_compaction(trajopt_handle* h, int min_batch, int ratio);
  * Defaults 0, 1. */
 int trajopt_set_sweep(trajopt_handle* h, int variant, int lanes);
 
+/* Line searches (single shooting, traopt_controller.py:1972-1990; multiple shooting with line_search, :2549-2590) try the
+ * step sizes alphas[0], alphas[1], ... in order and accept the first that passes.  Large batches roll out alphas[0] for
+ * everybody, then the rest for the problems that rejected it, then the accepted one again to keep its trajectory.  While
+ * the batch (padded to 32) is <= max_batch one launch rolls out EVERY step size and keeps every candidate trajectory
+ * (n_alphas x the trajectory memory): a solve of a few problems costs its number of dependent rollouts.  Same decisions,
+ * bit-identical results.  Default 256; 0 = never. */
+int trajopt_set_line_search_batch(trajopt_handle* h, int max_batch);
+
 #ifdef __cplusplus
 }
 #endif

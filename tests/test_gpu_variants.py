@@ -276,3 +276,30 @@ def test_augmented_lagrangian_with_velocity_bounds():
         assert np.max(np.abs(lm - r.lmbd)) < 1e-5 * max(1.0, np.max(np.abs(r.lmbd)))
         active |= r.outer_iterations > 1 and np.max(r.lmbd[:, 12:]) > 0
     assert active, "the velocity bounds never became active"
+
+
+@pytest.mark.parametrize("name,method,kw", [("se3_n120", "ss", {}), ("drone_n150", "ss", {}), ("so3_n249", "ss", {}),
+                                             ("se3_n120", "ms", {"line_search": True}),
+                                             ("so3_n249", "ms", {"line_search": True})])
+def test_one_launch_line_search_is_bit_identical(name, method, kw):
+    """Small batches roll out every line-search step size in one launch and keep every candidate (the default up to 256
+    problems, so the rest of this suite already runs that way against the oracle); `set_line_search_batch(0)` restores the
+    three-pass scheme of the large batches (step size 0, then the rest, then the accepted one again).  Same decisions,
+    every export bit-identical — with per-problem horizons too."""
+    g = problems.load_golden(name)
+    B = 37
+    s, x0, N = gc.make_solver(g, method, B, horizon=60, max_iters=25, tol_grad_norm=1e-12, **kw)
+    X0 = gc.perturbed_x0(x0, B, scale=0.3)      # large perturbations: several problems reject the full step
+    for horizons in (None, [N - (b % 5) * 7 for b in range(B)]):
+        s.set_horizons(horizons)
+        ref = None
+        for max_batch in (0, 256):
+            s.set_line_search_batch(max_batch)
+            out = {k: v.cpu().numpy() for k, v in s.solve(X0).items()}
+            out.update({k: v.cpu().numpy() for k, v in s.export_hist().items()})
+            if ref is None:
+                ref = out
+                assert np.any(out["alpha_hist"] > 0), "every problem accepted the full step: the test exercises nothing"
+            for k in ref:
+                assert np.array_equal(ref[k], out[k]), (horizons is not None, max_batch, k)
+    s.set_line_search_batch(256)

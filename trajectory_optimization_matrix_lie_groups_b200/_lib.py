@@ -101,6 +101,7 @@ SYMBOLS = {
     "trajopt_set_profiling": (_I, [_P, _I]),
     "trajopt_set_compaction": (_I, [_P, _I, _I]),
     "trajopt_set_sweep": (_I, [_P, _I, _I]),
+    "trajopt_set_line_search_batch": (_I, [_P, _I]),
 }
 
 

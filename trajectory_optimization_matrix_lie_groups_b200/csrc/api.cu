@@ -143,6 +143,7 @@ int trajopt_destroy(trajopt_handle* h) {
     DeviceGuard guard(h->device);
     for (void* p : h->allocs) cudaFree(p);
     for (void* p : h->hist_allocs) if (p) cudaFree(p);
+    for (void* p : h->cand_allocs) if (p) cudaFree(p);
     void* stage[] = {h->s_x0, h->s_us0, h->s_xs, h->s_us, h->s_J, h->s_grad, h->s_def, h->s_iters, h->s_status, h->s_snap, h->d_late};
     for (void* p : stage) if (p) cudaFree(p);
     if (h->d_perm) cudaFree(h->d_perm);
@@ -237,6 +238,7 @@ int trajopt_set_params(trajopt_handle* h, const trajopt_params* p) {
     q.so3_terminal_quirk = on_so3(h->kind) ? 1 : 0;
     int rc = ensure_hist(h);
     if (rc) return rc;
+    if ((rc = ensure_cand(h))) return rc;
     h->have_params = true;
     h->begun = false;
     return 0;
@@ -816,6 +818,14 @@ int trajopt_set_sweep(trajopt_handle* h, int variant, int lanes) {
     h->sweep_variant = variant;
     h->sweep_lanes = lanes;
     return 0;
+}
+
+int trajopt_set_line_search_batch(trajopt_handle* h, int max_batch) {
+    if (!h) return fail(TRAJOPT_E_INVALID, "trajopt_set_line_search_batch: NULL handle");
+    if (max_batch < 0) return fail(TRAJOPT_E_INVALID, "trajopt_set_line_search_batch: max_batch must be >= 0");
+    DeviceGuard guard(h->device);
+    h->cand_max_batch = max_batch;
+    return h->have_params ? ensure_cand(h) : 0;
 }
 
 int trajopt_set_profiling(trajopt_handle* h, int enable) {

@@ -399,9 +399,12 @@ __global__ void __launch_bounds__(kB3Threads * G, 4 / G) k_backward3(const Param
     constexpr int NX = D::NX, NP = D::NP, NU = D::NU, NV = NX - NP, F = LR::LEN;
     extern __shared__ __align__(128) double sm_cta[];
     const int lane = threadIdx.x & 31;
-    const int warp = (threadIdx.x >> 5) & 1;
-    const int tid = threadIdx.x & (kB3Threads - 1);   // thread within its group
-    const int grp = threadIdx.x / kB3Threads;
+    // G = 4 (-DB3_WITH_G4, A/B): the roles alternate so that every scheduler hosts one warp of each role (warp w runs on
+    // scheduler w % 4): two warps of the same role in step on one scheduler want the same pipe at the same time
+    const int wq = threadIdx.x >> 5;
+    const int warp = (G == 4) ? ((wq & 1) ^ ((wq >> 2) & 1)) : (wq & 1);
+    const int tid = warp * 32 + lane;                 // thread within its group
+    const int grp = wq >> 1;
     double* sm = sm_cta + (size_t)grp * (SM::GROUP_BYTES / 8);
     const int b = (blockIdx.x * G + grp) * 32 + lane;
     const int N = prm.N, Np1 = N + 1;     // record layout / loop extent; the problem's own horizon is Nb <= N

@@ -65,6 +65,9 @@ struct trajopt_handle {
     bool al_finished = false;
     bool al_inner_open = false;   // AL: an inner solve has been started and its multiplier update has not been applied yet
     int hist_cap = -1, cand_rows = -1;
+    // small batches with a line search: one trajectory buffer per step size (Work::Xc / Uc), see ensure_cand
+    void* cand_allocs[2] = {nullptr, nullptr};
+    int cand_alphas = 0, cand_max_batch = 256;
     // compaction: leading slots that may hold running problems; thresholds (see maybe_compact)
     int front = 0, compact_min_batch = 1024, compact_ratio = 4;
     // Nb / ref_batch are settings that outlive a solve ("set before trajopt_begin"); a compaction moves them with their
@@ -378,14 +381,25 @@ int inner_iteration(trajopt_handle* h, cudaStream_t s) {
     if (h->method == TRAJOPT_SS) {
         if ((rc = run_linearize<KIND, false>(h, s))) return rc;
         if ((rc = run_backward<KIND, false>(h, s, it))) return rc;
+        if (h->w.Xc) {
+            // small batch: the GPU is empty, so ONE launch rolls out every step size and keeps every candidate; what a solve
+            // costs here is the number of dependent rollouts (each a chain of N Exp / Log / f evaluations), and the tail of
+            // a single-shooting solve otherwise needs three per iteration
+            if ((rc = run_forward<KIND, false, true, true>(h, s, 0, na, -4, 0))) return rc;
+            LAUNCH(k_ls_select_ss, bgrid, 128, 0, s, h->prm, h->w, it, 0, na, 1);
+            LAUNCH((k_ls_copy_cand<KIND>), dim3(bgrid, h->N + 1), 128, 0, s, h->prm, h->w);
+            LAUNCH(k_ls_commit_ss, bgrid, 128, 0, s, h->prm, h->w, it);
+            h->it = h->it + 1;
+            return 0;
+        }
         // line search (:1972-1990): step size 0 first (accepted by nearly every problem), then
         // all remaining step sizes at once for the problems that rejected it
         if ((rc = run_forward<KIND, false, true, true>(h, s, 0, 1, -2, 0))) return rc;
         LAUNCH(k_ls_select_ss, bgrid, 128, 0, s, h->prm, h->w, it, 0, 1, na == 1 ? 1 : 0);
         if (na > 1) {
-            if ((rc = run_forward<KIND, false, false, true>(h, s, 1, na - 1, -1, 0))) return rc;
+            if ((rc = run_forward<KIND, false, true, true>(h, s, 1, na - 1, -1, 0))) return rc;      // costs only
             LAUNCH(k_ls_select_ss, bgrid, 128, 0, s, h->prm, h->w, it, 1, na - 1, 1);
-            if ((rc = run_forward<KIND, false, true, false>(h, s, 1, 1, -3, 1))) return rc;
+            if ((rc = run_forward<KIND, false, true, true>(h, s, 1, 1, -3, 1))) return rc;            // the accepted one, kept
         }
         LAUNCH(k_ls_commit_ss, bgrid, 128, 0, s, h->prm, h->w, it);
     } else {
@@ -398,12 +412,20 @@ int inner_iteration(trajopt_handle* h, cudaStream_t s) {
                     PhaseTimer t(h, s, PH_FWD);
                     LAUNCH((k_ms_expected<KIND>), h->Bp / kBlock, kBlock, 0, s, h->prm, h->w, h->d_dweight);
                 }
+                if (h->w.Xc) {   // small batch: every step size in one launch (see the single-shooting branch)
+                    if ((rc = run_forward<KIND, true, true, true>(h, s, 0, na, -4, 0))) return rc;
+                    LAUNCH(k_ls_select_ms, bgrid, 128, 0, s, h->prm, h->w, it, 0, na, 1);
+                    LAUNCH((k_ls_copy_cand<KIND>), dim3(bgrid, h->N + 1), 128, 0, s, h->prm, h->w);
+                    LAUNCH(k_ls_commit_ms, bgrid, 128, 0, s, h->prm, h->w, it);
+                    h->it = h->it + 1;
+                    return 0;
+                }
                 if ((rc = run_forward<KIND, true, true, true>(h, s, 0, 1, -2, 0))) return rc;
                 LAUNCH(k_ls_select_ms, bgrid, 128, 0, s, h->prm, h->w, it, 0, 1, na == 1 ? 1 : 0);
                 if (na > 1) {
-                    if ((rc = run_forward<KIND, true, false, true>(h, s, 1, na - 1, -1, 0))) return rc;
+                    if ((rc = run_forward<KIND, true, true, true>(h, s, 1, na - 1, -1, 0))) return rc;
                     LAUNCH(k_ls_select_ms, bgrid, 128, 0, s, h->prm, h->w, it, 1, na - 1, 1);
-                    if ((rc = run_forward<KIND, true, true, false>(h, s, 1, 1, -3, 1))) return rc;
+                    if ((rc = run_forward<KIND, true, true, true>(h, s, 1, 1, -3, 1))) return rc;
                 }
                 LAUNCH(k_ls_commit_ms, bgrid, 128, 0, s, h->prm, h->w, it);
             } else {
@@ -712,6 +734,35 @@ inline int ensure_hist(trajopt_handle* h) {
     return 0;
 }
 
+
+// Candidate trajectory buffers of the one-launch line search: only where a line search runs (single shooting, multiple
+// shooting with line_search), more than one step size, and a batch small enough that n_alphas rollouts side by side still
+// leave the GPU under-filled (<= cand_max_batch slots; TRAJOPT_LS_ALL_BATCH overrides, 0 disables).
+inline int ensure_cand(trajopt_handle* h) {
+    static const int env_max = [] { const char* e = getenv("TRAJOPT_LS_ALL_BATCH"); return e ? atoi(e) : -1; }();
+    const int max_batch = env_max >= 0 ? env_max : h->cand_max_batch;
+    const bool ls = h->method == TRAJOPT_SS || (h->method != TRAJOPT_SS && h->prm.line_search);
+    const int want = (ls && h->prm.n_alphas > 1 && h->Bp <= max_batch) ? h->prm.n_alphas : 0;
+    if (want == h->cand_alphas) return 0;
+    for (void*& p : h->cand_allocs) {
+        if (p) cudaFree(p);
+        p = nullptr;
+    }
+    h->w.Xc = h->w.Uc = nullptr;
+    h->cand_alphas = 0;
+    if (want) {
+        const size_t Bp = (size_t)h->Bp;
+        const size_t sz[2] = {(size_t)want * (h->N + 1) * h->NS * Bp * 8, (size_t)want * h->N * h->NU * Bp * 8};
+        for (int i = 0; i < 2; ++i) {
+            CUDA_OK(cudaMalloc(&h->cand_allocs[i], sz[i]));
+            CUDA_OK(cudaMemset(h->cand_allocs[i], 0, sz[i]));
+        }
+        h->w.Xc = (double*)h->cand_allocs[0];
+        h->w.Uc = (double*)h->cand_allocs[1];
+        h->cand_alphas = want;
+    }
+    return 0;
+}
 
 }  // namespace trajopt_host
 

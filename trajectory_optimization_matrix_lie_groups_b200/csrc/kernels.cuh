@@ -60,6 +60,10 @@ struct Work {
     int* scnt;           // [4] free slots, finished problems to export, running slots
     int* Nb;             // [Bp] horizon of each problem, 1 <= Nb <= N (trajopt_set_horizons; default N for all)
     int* orig;           // [Bp] slot -> problem index of the caller (identity until a compaction moves problems)
+    // small batches (ensure_cand): one trajectory buffer per line-search step size, so that ONE launch rolls out and keeps
+    // every candidate ([n_alphas][N+1][NS][Bp], [n_alphas][N][NU][Bp]); NULL otherwise
+    double* Xc;
+    double* Uc;
 };
 
 constexpr int kBlock = 32;

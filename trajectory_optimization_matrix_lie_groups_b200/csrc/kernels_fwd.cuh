@@ -20,6 +20,12 @@ namespace trajopt {
 //   COST   : accumulate J_new = sum_i l(x_new_i, u_new_i) + l_N left to right (:2084-2096);
 //            MS additionally accumulates the candidate's defect norm (:2565-2566)
 // Which problems run: `need` < 0 -> every running problem; otherwise those with ls_state == need.
+// The three passes of a line search (step size 0; the remaining ones; the accepted one again) all run the WRITE && COST
+// instantiation, so that a candidate's cost and its kept trajectory come from the same instruction sequence whichever
+// pass produced them (separate instantiations may contract a * b + c * d differently); the pass that only needs costs
+// (need == -1) skips the stores at run time.
+// need == -4 (small batches, WRITE && COST): every candidate keeps its trajectory in ITS OWN buffer (Work::Xc / Uc) so that
+// one launch serves the whole line search; k_ls_copy_cand then moves the accepted one into the problem's other buffer.
 // ------------------------------------------------------------------------------------------
 // value of the AL terms of the velocity bounds at (stage, problem) for velocity xi
 template <int KIND>
@@ -74,7 +80,12 @@ __global__ void __launch_bounds__(kBlock) k_forward(const Params prm, Work w, in
     const double* U = w.U[cur];
     double* Xn = w.X[1 - cur];
     double* Un = w.U[1 - cur];
+    if (WRITE && COST && need == -4) {
+        Xn = w.Xc + (size_t)ai * (size_t)(N + 1) * D::NS * Bp;
+        Un = w.Uc + (size_t)ai * (size_t)N * NU * Bp;
+    }
     const double* lin = w.lin;
+    const bool store = WRITE && !(COST && need == -1);
 
     // gains of the warp's 32 problems, one stage at a time, double-buffered by one TMA bulk copy per stage (as in
     // k_forward_ms_full); the lanes that do not run keep the warp's staging company
@@ -95,7 +106,7 @@ __global__ void __launch_bounds__(kBlock) k_forward(const Params prm, Work w, in
     State<KIND> xnew, x, xnext;
     load_state<KIND>(X, 0, Bp, b, x);
     xnew = x;
-    if (WRITE && run) store_state<KIND>(Xn, 0, Bp, b, xnew);
+    if (store && run) store_state<KIND>(Xn, 0, Bp, b, xnew);
     double J = 0.0, dsq = 0.0;
     const int Nb = w.Nb[b];              // this problem's horizon (<= N)
     int Nmax = run ? Nb : 0;             // stages the warp stays together for
@@ -123,7 +134,7 @@ __global__ void __launch_bounds__(kBlock) k_forward(const Params prm, Work w, in
             du[a] = s;
             unew[a] = u[a] + s;
         }
-        if (WRITE) {
+        if (store) {
 #pragma unroll
             for (int a = 0; a < NU; ++a) Un[soa(i, a, NU, Bp, b)] = unew[a];
         }
@@ -212,7 +223,7 @@ __global__ void __launch_bounds__(kBlock) k_forward(const Params prm, Work w, in
 #pragma unroll
             for (int j = 0; j < NX; ++j) dsq += dd[j] * dd[j];
         }
-        if (WRITE) store_state<KIND>(Xn, i + 1, Bp, b, xn1);
+        if (store) store_state<KIND>(Xn, i + 1, Bp, b, xn1);
         xnew = xn1;
         x = xnext;
         }   // run && i < Nb
@@ -398,6 +409,28 @@ static __global__ void k_ls_select_ss(const Params prm, Work w, int it_arg, int 
     }
     const unsigned m = __ballot_sync(0xffffffffu, pending);
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(&w.counters[1], __popc(m));
+}
+
+// small batches: the accepted candidate's trajectory (kept by k_forward, need == -4) -> the problem's other buffer.
+// thread = (problem, stage); rows beyond the problem's horizon were not written and are not copied.
+template <int KIND>
+__global__ void k_ls_copy_cand(const Params prm, Work w) {
+    using D = Dims<KIND>;
+    const int b = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    if (b >= prm.B || w.status[b] != TRAJOPT_RUNNING) return;
+    const int a = w.ls_state[b];
+    if (a < 0 || i > w.Nb[b]) return;
+    const int Bp = prm.Bp, N = prm.N, other = 1 - w.sel[b];
+    const double* xs = w.Xc + (size_t)a * (size_t)(N + 1) * D::NS * Bp;
+    double* xd = w.X[other];
+#pragma unroll
+    for (int f = 0; f < D::NS; ++f) xd[soa(i, f, D::NS, Bp, b)] = xs[soa(i, f, D::NS, Bp, b)];
+    if (i < w.Nb[b]) {
+        const double* us = w.Uc + (size_t)a * (size_t)N * D::NU * Bp;
+        double* ud = w.U[other];
+#pragma unroll
+        for (int f = 0; f < D::NU; ++f) ud[soa(i, f, D::NU, Bp, b)] = us[soa(i, f, D::NU, Bp, b)];
+    }
 }
 
 // commit an accepted SS candidate whose trajectory is in the other buffer

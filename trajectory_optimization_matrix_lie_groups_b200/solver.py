@@ -370,6 +370,10 @@ class BatchSolver:
         """Pack the running problems into the leading slots once running * ratio <= slots in use (min_batch < 0: never)."""
         check(lib.trajopt_set_compaction(self._h, int(min_batch), int(ratio)))
 
+    def set_line_search_batch(self, max_batch=256):
+        """One launch rolls out every line-search step size while the padded batch is <= max_batch (0: never)."""
+        check(lib.trajopt_set_line_search_batch(self._h, int(max_batch)))
+
     def set_sweep(self, variant=0, lanes=1):
         """Backward-sweep mapping: 0 automatic, 2 / 4 / 6 = always two- / four- / six-warp CTAs; lanes = solvers sharing this GPU."""
         check(lib.trajopt_set_sweep(self._h, int(variant), int(lanes)))
