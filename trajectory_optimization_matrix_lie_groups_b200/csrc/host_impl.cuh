@@ -647,8 +647,12 @@ int iterate_impl(trajopt_handle* h, int n_iters, int* n_active_out, cudaStream_t
         {
             PhaseTimer t(h, s, PH_OTHER);
             CUDA_OK(cudaMemsetAsync(h->w.counters, 0, 4 * sizeof(int), s));
-            LAUNCH((k_al_update<KIND>), blocks_for(h->Bp, 128), 128, 0, s, h->prm, h->w, h->user.tol_constr,
-                   h->user.al_mu_scale, h->user.al_mu_max, h->al_outer);
+            const int bgrid = blocks_for(h->Bp, 128);
+            const dim3 sgrid(bgrid, blocks_for(h->N + 1, kAlChunk));
+            LAUNCH(k_al_viol_zero, bgrid, 128, 0, s, h->prm, h->w);
+            LAUNCH((k_al_viol<KIND>), sgrid, 128, 0, s, h->prm, h->w);
+            LAUNCH(k_al_decide, bgrid, 128, 0, s, h->prm, h->w, h->user.tol_constr, h->user.al_mu_scale, h->user.al_mu_max, h->al_outer);
+            LAUNCH((k_al_apply<KIND>), sgrid, 128, 0, s, h->prm, h->w);
             LAUNCH(k_publish4, 1, 32, 0, s, (const int*)h->w.counters, (volatile int*)h->h_counters_dev);
             CUDA_OK(cudaStreamSynchronize(s));
         }

@@ -8,7 +8,7 @@
 //   k_forward     problem-parallel rollout (one step size per thread).          :2030-2082 / 2641-2740
 //   k_init_*      initial rollout :2015-2028 / initial guess :3123-3136
 //   k_ls_*        line-search bookkeeping (accept first J_new < J_opt)          :1972-1990
-//   k_al_update   multiplier / penalty update                                   :3270-3290
+//   k_al_*        multiplier / penalty update (stage-parallel)                  :3270-3290
 #pragma once
 #include "model.cuh"
 
