@@ -58,6 +58,11 @@ namespace trajopt {
 // marks and runs 4 % FASTER without them (131072 x 150: 240.1 against 250.7 ms for the 27 sweeps of a solve); the
 // six-input families spill 580-850 bytes without them.
 __host__ __device__ constexpr bool b3_marks(int kind) { return kind != TRAJOPT_DRONE; }
+// which warp of a group forms and stores the feed-forward gain k (A/B: -DB3_KFF_WARP=1)
+#ifndef B3_KFF_WARP
+#define B3_KFF_WARP 0
+#endif
+constexpr int kB3KffWarp = B3_KFF_WARP;
 constexpr int kB3Warps = 2;
 constexpr int kB3Threads = kB3Warps * 32;
 
@@ -540,6 +545,17 @@ __global__ void __launch_bounds__(kB3Threads * G, 4 / G) k_backward3(const Param
             }
         }
 
+#ifdef B3_L1_PREFETCH
+        {   // A/B: the stage's l_x / l_xx rows (read straight from global memory further down) towards L1
+            const char* lxrow = (const char*)(group_base + (size_t)i * kStageDoubles + (size_t)LR::LX_OFF * 32);
+            constexpr int kLines = (NX + LR::LXX_LEN) * 2;
+#pragma unroll
+            for (int t = 0; t < (kLines + kB3Threads - 1) / kB3Threads; ++t) {
+                const int line = t * kB3Threads + tid;
+                if (line < kLines) asm volatile("prefetch.global.L1 [%0];" ::"l"(lxrow + (size_t)line * 128));
+            }
+        }
+#endif
         // ---- (S0a) Q_uu0 = l_uu + Bv^T V_vv Bv and its regularised Cholesky factor (every warp) -------
         double Lc[NU * NU];   // lower factor, Lc[r][c] for c < r; the diagonal stores 1 / L_rr
         double mu_used;
@@ -660,7 +676,7 @@ __global__ void __launch_bounds__(kB3Threads * G, 4 / G) k_backward3(const Param
                 for (int k = 0; k < r; ++k) s = fma(-Lc[r * NU + k], y[k], s);
                 y[r] = s * Lc[r * NU + r];
             }
-            if (warp == 0) {
+            if (warp == kB3KffWarp) {
                 double kk[NU];
 #pragma unroll
                 for (int r = NU - 1; r >= 0; --r) {
