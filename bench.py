@@ -238,7 +238,19 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def load_kernel_counters(kind):
+def sweep_kernel_name(kind, B):
+    """the Riccati sweep the profiled solve (one batch alone) launches at this batch size: run_backward, host_impl.cuh"""
+    if kind in ("so3", "pendulum"):
+        return "k_backward (Riccati sweep, one warp per 32 problems)"
+    slots = (B + 31) // 32 * 32
+    if slots <= 148 * 32:
+        return "k_backward6 (Riccati sweep, 6-warp CTA per 32 problems: serial part on its own warps)"
+    if slots <= 148 * 2 * 32:
+        return "k_backward4 (Riccati sweep, 4-warp CTA per 32 problems)"
+    return "k_backward3 (Riccati sweep, 2-warp CTA per 32 problems; the tail launches after compaction run k_backward4 / k_backward6)"
+
+
+def load_kernel_counters(kind, B=1 << 30):
     """ncu-derived static counters of the dominant kernel (profiles/kernel_counters.json, written from a committed
     `ncu --set full` capture by scripts/ncu_summary.py): executed FP64 thread-instructions and DRAM bytes per launch and
     the stage-iterations that launch processed."""
@@ -246,7 +258,10 @@ def load_kernel_counters(kind):
     if not os.path.exists(path):
         return None
     with open(path) as f:
-        return json.load(f).get({"se3": "k_backward3_se3", "rigid": "k_backward3_se3", "drone": "k_backward3_drone"}.get(kind, "k_backward_so3"))
+        table = json.load(f)
+    slots = (B + 31) // 32 * 32
+    se3 = "k_backward6_se3_2048" if slots <= 148 * 32 else ("k_backward4_se3_2048" if slots <= 148 * 64 else "k_backward3_se3")
+    return table.get({"se3": se3, "rigid": se3, "drone": "k_backward3_drone"}.get(kind, "k_backward_so3"))
 
 
 def measure_host_d2h(torch, dist, dev, world, gib=1.0, reps=3):
@@ -602,7 +617,7 @@ def run_gpu_arm(args):
         rollouts = float(fwd_n) * B
     flop_bwd = model["flop_bwd"] * wl.N * sweeps
     achieved = flop_bwd / (bwd_ms * 1e-3) / 1e12 if bwd_ms > 0 else 0.0
-    counters = load_kernel_counters(wl.kind)
+    counters = load_kernel_counters(wl.kind, B)
     traffic = executed = None
     if counters:
         traffic = counters.get("dram_bytes_per_launch")
@@ -635,7 +650,7 @@ def run_gpu_arm(args):
                                  "leg's trajectory copies share"},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "fp64", "kernel": "k_backward3 (Riccati sweep, 2-warp CTA per 32 problems)" if wl.kind not in ("so3", "pendulum") else "k_backward (Riccati sweep)", "achieved": achieved, "peak": peak,
+        "roofline": {"bound": "fp64", "kernel": sweep_kernel_name(wl.kind, B), "achieved": achieved, "peak": peak,
                      "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": traffic,
                      "frac_note": "model fraction: SURVEY 8d's DENSE flop count per stage-iteration over the measured time; the kernel "
                                   "skips the structural zeros of f_x / f_u, see executed_frac for the FLOPs it actually issues",
