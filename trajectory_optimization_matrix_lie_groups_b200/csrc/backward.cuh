@@ -80,9 +80,40 @@ TO_DEV void load_blk(const double* __restrict__ rec, size_t Bp, double (&m)[9]) 
     }
 }
 
-template <int KIND> constexpr int bwd_smem_doubles() {
+template <int KIND> __host__ __device__ constexpr int bwd_smem_doubles() {
     using D = Dims<KIND>;
     return D::NX * (D::NX + 1) + D::NU * (D::NX - 3) + D::NX;
+}
+// + the whole linearisation record of one stage of the warp's 32-problem group, double-buffered (TMA), + two mbarriers
+template <int KIND, int LPW> constexpr size_t bwd_smem_bytes() {
+    return ((size_t)bwd_smem_doubles<KIND>() * LPW + 2 * (size_t)LinRec<KIND>::LEN * 32) * sizeof(double) + 16;
+}
+
+// mbarrier / TMA bulk copy (cp.async.bulk) helpers shared by the sweeps and the rollouts
+__device__ __forceinline__ uint32_t b3_smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void b3_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void b3_tma_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void b3_mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    }
 }
 
 // LPW = problems (active lanes) per warp: 32, or 16 to double the number of independent recursions in flight
@@ -95,48 +126,75 @@ __global__ void __launch_bounds__(LPW) k_backward(const Params prm, Work w, int 
     constexpr int NT = NX * (NX + 1) / 2;
     constexpr int NB = NX / 3;       // 3x3 blocks per side
     constexpr int NYC = NX - 3;      // columns of Y kept in shared memory
-    extern __shared__ double sm[];
+    extern __shared__ __align__(128) double sm[];
     const int lane = threadIdx.x;
     const int b = blockIdx.x * LPW + lane;
-    if (b >= prm.B || w.status[b] != TRAJOPT_RUNNING) return;
-    const int it = it_arg >= 0 ? it_arg : w.iters[b];   // < 0: every slot counts its own iterations (trajopt_solve_stream)
+    // every lane stays for the warp-wide record staging; `act` = this lane's problem takes part in the sweep
+    bool act = (b < prm.B) && (w.status[b] == TRAJOPT_RUNNING);
+    const int it = it_arg >= 0 ? it_arg : (act ? w.iters[b] : 0);   // < 0: every slot counts its own iterations (trajopt_solve_stream)
     const int N = prm.N;                 // record layout stride; the problem's own horizon is Nb
-    const int Nb = w.Nb[b];
+    const int Nb = w.Nb[b < prm.Bp ? b : 0];
     const size_t Bp = (size_t)prm.Bp;
     double* Vs = sm + lane;
     double* Vn = sm + NT * LPW + lane;
     double* Ys = sm + 2 * NT * LPW + lane;
     double* Vxs = sm + (2 * NT + NU * NYC) * LPW + lane;
+    double* recbuf = sm + (size_t)bwd_smem_doubles<KIND>() * LPW;      // 2 x [LEN][32]
+    const uint32_t bar0 = b3_smem_addr(recbuf + 2 * (size_t)F * 32);
     const double* __restrict__ lin = w.lin;
 
     // ---- cost / defect of the current trajectory ----------------------------------------
-    double Jcur, dn = 0.0;
-    if constexpr (MS) {
-        // J_new of the previous iteration: Python sum, left to right, + terminal (:2742-2754)
-        double s = 0.0;
-        for (int i = 0; i < Nb; ++i) s += w.Lc[(size_t)i * Bp + b];
-        Jcur = s + w.Lc[(size_t)Nb * Bp + b];
-        double q = 0.0;
-        for (int i = 0; i < Nb; ++i) q += w.Dsq[(size_t)i * Bp + b];
-        dn = sqrt(q);
-        w.dnorm[b] = dn;
-        if (it > 0) w.Jhist[(size_t)(it - 1) * Bp + b] = Jcur;
-        w.defhist[(size_t)it * Bp + b] = dn;
-    } else {
-        Jcur = pairwise_sum(w.Lc + b, Bp, Nb + 1);     // J_opt = L.sum() (:1935)
+    double Jcur = 0.0, dn = 0.0;
+    if (act) {
+        if constexpr (MS) {
+            // J_new of the previous iteration: Python sum, left to right, + terminal (:2742-2754)
+            double s = 0.0;
+            for (int i = 0; i < Nb; ++i) s += w.Lc[(size_t)i * Bp + b];
+            Jcur = s + w.Lc[(size_t)Nb * Bp + b];
+            double q = 0.0;
+            for (int i = 0; i < Nb; ++i) q += w.Dsq[(size_t)i * Bp + b];
+            dn = sqrt(q);
+            w.dnorm[b] = dn;
+            if (it > 0) w.Jhist[(size_t)(it - 1) * Bp + b] = Jcur;
+            w.defhist[(size_t)it * Bp + b] = dn;
+        } else {
+            Jcur = pairwise_sum(w.Lc + b, Bp, Nb + 1);     // J_opt = L.sum() (:1935)
+        }
+        w.J[b] = Jcur;
+        if (!isfinite(Jcur)) {
+            w.status[b] = TRAJOPT_NO_DESCENT | TRAJOPT_FLAG_NONFINITE;
+            act = false;
+        } else if (it >= prm.max_iters) {          // MS only: closing pass after the last rollout
+            w.status[b] = TRAJOPT_MAX_ITER | (w.status[b] & ~15);
+            act = false;
+        }
     }
-    w.J[b] = Jcur;
-    if (!isfinite(Jcur)) {
-        w.status[b] = TRAJOPT_NO_DESCENT | TRAJOPT_FLAG_NONFINITE;
-        return;
+    const bool was_running = act;
+    // stages the warp stays together for (per-problem horizons); nobody left: the warp leaves
+    int Nmax = act ? Nb : 0;
+#pragma unroll
+    for (int o = LPW / 2; o > 0; o >>= 1) Nmax = max(Nmax, __shfl_xor_sync(0xffffffffu >> (32 - LPW), Nmax, o));
+    if (Nmax == 0) return;
+
+    // The record of a stage of the warp's group (one contiguous chunk, see LinRec) arrives by ONE TMA bulk copy, two stages
+    // ahead, double-buffered: the recursion never waits on global memory for it.  (Until round 2 this kernel read the
+    // record straight from L2 inside the stage: 2.9 us per stage of a 6-dimensional problem, most of it load latency.)
+    const double* group_base = lin + lsoa(0, 0, F, N + 1, b - (b & 31));
+    constexpr uint32_t kRecBytes = (uint32_t)F * 32 * 8;
+    if (lane == 0) {
+        b3_mbar_init(bar0, 1);
+        b3_mbar_init(bar0 + 8, 1);
     }
-    if (it >= prm.max_iters) {          // MS only: closing pass after the last rollout
-        w.status[b] = TRAJOPT_MAX_ITER | (w.status[b] & ~15);
-        return;
-    }
+    __syncwarp(0xffffffffu >> (32 - LPW));
+    auto issue = [&](int stage, int buf) {
+        if (lane == 0)
+            b3_tma_load(b3_smem_addr(recbuf + (size_t)buf * F * 32), group_base + (size_t)stage * F * 32, kRecBytes, bar0 + 8 * buf);
+    };
+    issue(Nmax - 1, 0);
+    if (Nmax > 1) issue(Nmax - 2, 1);
 
     // ---- terminal condition: V_x = l_x(N), V_xx = l_xx(N) --------------------------------
-    {
+    if (act) {
         const double* rec = lin + lsoa(Nb, 0, F, N + 1, b);
 #pragma unroll
         for (int j = 0; j < NX; ++j) Vxs[j * LPW] = rec[(size_t)(LR::LX_OFF + j) * kRecStride];
@@ -154,28 +212,23 @@ __global__ void __launch_bounds__(LPW) k_backward(const Params prm, Work w, int 
     double pad[NX];                      // SS: adjoint variable p (:2339)
     if constexpr (!MS) {
 #pragma unroll
-        for (int j = 0; j < NX; ++j) pad[j] = Vxs[j * LPW];
+        for (int j = 0; j < NX; ++j) pad[j] = act ? Vxs[j * LPW] : 0.0;
     }
 
-    double mu = w.mu[b], delta = w.delta[b];
+    double mu = 0.0, delta = 0.0;
+    if (act) {
+        mu = w.mu[b];
+        delta = w.delta[b];
+    }
     double gsum = 0.0;
     int flags = 0;
 
-    for (int i = N - 1; i >= 0; --i) {
-        if (i >= Nb) continue;           // stages beyond this problem's horizon
-        const double* __restrict__ rec = lin + lsoa(i, 0, F, N + 1, b);
+    for (int i = Nmax - 1; i >= 0; --i) {
+        const int use = Nmax - 1 - i, buf = use & 1;
+        b3_mbar_wait(bar0 + 8 * buf, (uint32_t)((use >> 1) & 1));      // this stage's record is in shared memory
+        if (act && i < Nb) do {          // stages beyond this problem's horizon only keep the warp company
+        const double* __restrict__ rec = recbuf + (size_t)buf * F * 32 + (b & 31);
         const BvStage<KIND> Bv(prm, rec, kRecStride);   // velocity rows of f_u: constant, or per stage (pendulum)
-        if (i > 0) {   // pull the next record towards L2 while this stage computes
-            const char* nxt = (const char*)(lin + lsoa(i - 1, 0, F, N + 1, b - lane));
-#pragma unroll
-            for (int t = 0; t < (F * 2 + LPW - 1) / LPW; ++t) {
-                const int line = t * LPW + lane;
-                if (line < F * 2) {
-                    const char* p = nxt + (size_t)line * 128;
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-                }
-            }
-        }
 
         // (1) v = V_x + V_xx d
         double v[NX];
@@ -340,6 +393,7 @@ __global__ void __launch_bounds__(LPW) k_backward(const Params prm, Work w, int 
             // The reference warns and carries on with a non-PD Q_uu (:2238-2240); such a problem
             // has already diverged.  It is stopped here and flagged.
             flags |= TRAJOPT_FLAG_REG_EXCEEDED;
+            act = false;
             break;
         }
 
@@ -507,8 +561,12 @@ __global__ void __launch_bounds__(LPW) k_backward(const Params prm, Work w, int 
             }
         });
         { double* t = Vs; Vs = Vn; Vn = t; }
+        } while (0);
+        __syncwarp(0xffffffffu >> (32 - LPW));          // every lane is done with this buffer
+        if (i >= 2) issue(i - 2, buf);
     }
 
+    if (!was_running) return;
     w.mu[b] = mu;
     w.delta[b] = delta;
     const double g = gsum / (double)Nb;

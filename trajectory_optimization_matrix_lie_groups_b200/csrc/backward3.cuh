@@ -83,32 +83,7 @@ template <int KIND> struct B3Smem {
 
 __host__ __device__ constexpr int b3_ycol(int c) { return c < 6 ? c : c - 3; }   // smem slot of Y column c (c in 0..5, 9..11)
 
-// ---- mbarrier / TMA bulk copy ----------------------------------------------------------------
-__device__ __forceinline__ uint32_t b3_smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void b3_mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void b3_tma_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
-}
-__device__ __forceinline__ void b3_mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done = 0;
-    while (!done) {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-    }
-}
+// (mbarrier / TMA bulk copy helpers: backward.cuh)
 
 // ---- building blocks ----------------------------------------------------------------------------
 // Plain fully-unrolled loops: after unrolling every index, block kind and record offset is a

@@ -328,7 +328,7 @@ int run_backward(trajopt_handle* h, cudaStream_t s, int it) {
             return launch(k_backward3<KIND, MS, false, 1>, 1);
         }
     }
-    constexpr size_t smem = (size_t)bwd_smem_doubles<KIND>() * kBlock * sizeof(double);
+    constexpr size_t smem = bwd_smem_bytes<KIND, kBlock>();
     { int rc_ = ensure_smem(h, k_backward<KIND, MS, kBlock>, smem); if (rc_) return rc_; }
     LAUNCH((k_backward<KIND, MS, kBlock>), h->Bp / kBlock, kBlock, smem, s, h->prm, h->w, it);
     return 0;
