@@ -70,7 +70,9 @@ def test_argument_validation_needs_no_gpu():
     assert h.value is None
     for fn, args in (("trajopt_begin", (None, None, None, 0, None)), ("trajopt_iterate", (None, 1, None, None)),
                      ("trajopt_set_params", (None, None)), ("trajopt_set_reference", (None, None, None)),
-                     ("trajopt_export", (None,) * 9), ("trajopt_solve_host", (None,) * 3 + (0,) + (None,) * 8)):
+                     ("trajopt_export", (None,) * 9), ("trajopt_solve_host", (None,) * 3 + (0,) + (None,) * 8),
+                     ("trajopt_set_sweep", (None, 6, 1)), ("trajopt_set_line_search_batch", (None, 256)),
+                     ("trajopt_set_compaction", (None, 1024, 4))):
         assert getattr(lib, fn)(*args) == -1, fn
     assert lib.trajopt_destroy(None) == 0
     assert lib.trajopt_launch_count(1) >= 0
