@@ -2,7 +2,7 @@
 // solve, a strong-scaling shard of <= 148 x 32 problems, the last tail iterations of a batch): one CTA of SIX warps per
 // group, lane = problem.  Same recursion and — operation for operation — the same arithmetic as k_backward3 / k_backward4
 // (traopt_controller.py:2178-2321 / 2912-3068, gradient norms :2323-2349 / :3070-3093): every output element comes from
-// the same building block (b3_compute_X, b3_gains, b3_block_cb/rb ...) with the same inputs, so the three sweeps are
+// the same building block (b3_compute_X, b3_block_cb/rb, the two halves of b3_gains ...) with the same inputs, so the three sweeps are
 // bit-identical and the host picks one launch by launch (run_backward, host_impl.cuh).
 //
 // What a launch costs in this regime is the LENGTH of a stage's longest dependent instruction stream, not throughput.
@@ -10,11 +10,14 @@
 // Cholesky factor with six dependent rsqrt, y = L^-1 Q_u): ~2.5 k of the ~5.8 k statically scheduled cycles of a
 // four-warp stage.  Here that part gets its own two warps and runs BESIDE the column work that does not need it:
 //
-//            until barrier (F)                  | until barrier (A)                         | until barrier (B)
-//   warp c   X_c = V A[:,c], Q_x part of V_x     | y, Y_c = L^-1 Q_ux, K_c, V_x, V(c,c)       | one off-diagonal block of V
-//   warp 4   Q_uu0, Cholesky (mu, delta state)   | SS: adjoint p                              | V(0,2)
-//   warp 5   v = V_x + V d, Q_u, |Q_u|           | y, k -> gains                              | V(1,2)
+//            until barrier (F)                           | until barrier (A)                          | until barrier (B)
+//   warp c   X_c = V A[:,c], Q_x part of V_x, Q_ux[:,c],  | y, Y_c = L^-1 Q_ux, K_c, V_x,               | one off-diagonal block of V
+//            l_xx + A[:,c]^T X_c of V(c,c)                | V(c,c) -= Y_c^T Y_c                          |
+//   warp 4   Q_uu0, Cholesky (mu, delta state)            | SS: adjoint p                                | V(0,2)
+//   warp 5   v = V_x + V d, Q_u, |Q_u|                    | y, k -> gains                                | V(1,2)
 //
+// (what a column warp finishes before (F) is pinned there with empty asm statements: left alone, ptxas sinks those
+// register-only computations behind the barrier, i.e. back onto the critical path.)
 // (F): the factor L, Q_u and mu go through shared memory.  (A): every X is formed and every Y is visible, V and V_x are
 // overwritten in place.  X_2, X_3 and Y_2 also go through shared memory so that the six off-diagonal blocks are one per
 // warp: V(0,3) warp 0, V(0,1) warp 1, V(2,3) warp 2 (= X_2^T A[:,3]), V(1,3) warp 3.  One CTA per SM leaves room to stage
